@@ -1,0 +1,87 @@
+"""ctypes binding of libcaptra_ops.so -- the ONLY compute path of this package.
+
+There is deliberately no fallback: if the library is missing or an op is handed a non-CUDA
+tensor the call raises.  (The CPU restatement lives under oracle/ and is test infrastructure.)
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcaptra_ops.so")
+
+_lib = None
+
+c_int, c_i64, c_float, c_void_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes; every entry returns int status.  Must list every symbol of
+# include/captra_ops.h (tests/test_abi.py checks the header against this table).
+_P = c_void_p
+SIGNATURES = {
+    "ball_query_kernel_launcher_fast": [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P],
+    "group_points_kernel_launcher_fast": [c_int] * 5 + [_P, _P, _P, _P],
+    "group_points_grad_kernel_launcher_fast": [c_int] * 5 + [_P, _P, _P, _P],
+    "gather_points_kernel_launcher_fast": [c_int] * 4 + [_P, _P, _P, _P],
+    "gather_points_grad_kernel_launcher_fast": [c_int] * 4 + [_P, _P, _P, _P],
+    "furthest_point_sampling_kernel_launcher": [c_int] * 3 + [_P, _P, _P, _P],
+    "three_nn_kernel_launcher_fast": [c_int] * 3 + [_P, _P, _P, _P, _P],
+    "knn_kernel_launcher_fast": [c_int] * 4 + [_P, _P, _P, _P, _P],
+    "three_interpolate_kernel_launcher_fast": [c_int] * 4 + [_P, _P, _P, _P, _P],
+    "three_interpolate_grad_kernel_launcher_fast": [c_int] * 4 + [_P, _P, _P, _P, _P],
+    "captra_ball_query_multi": [c_int] * 4 + [_P, _P, _P, _P, _P, _P],
+    "captra_fps_gather": [c_int] * 3 + [_P, _P, _P, _P, _P],
+    "captra_three_nn_interpolate": [c_int] * 4 + [_P] * 7 + [c_int, c_i64, c_int, _P],
+}
+OTHER_SYMBOLS = ["captra_last_error", "captra_abi_version", "captra_launch_count"]
+
+
+class CaptraError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libcaptra_ops.so (raises if it has not been built: run `python -m captra_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CaptraError(
+            "libcaptra_ops.so not found at %s -- build it with `python -m captra_b200.build` "
+            "(there is no CPU/eager fallback in this package)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    lib.captra_last_error.restype = ctypes.c_char_p
+    lib.captra_abi_version.restype = c_int
+    lib.captra_launch_count.restype = c_i64
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        raise CaptraError("%s failed (status %d): %s" % (what, status, load().captra_last_error().decode()))
+
+
+def launch_count():
+    return int(load().captra_launch_count())
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t, dtype=None, name="tensor"):
+    """Device pointer of a contiguous CUDA tensor (raises otherwise -- no silent copies)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CaptraError("%s must be a CUDA tensor (captra_b200 has no CPU path)" % name)
+    if not t.is_contiguous():
+        raise CaptraError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise CaptraError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.data_ptr()

@@ -1,0 +1,209 @@
+// fps.cu -- iterative furthest point sampling (reference: sampling_gpu.cu:86-209).
+//
+// The reference re-reads the cloud and its running min-distance array from global memory in
+// every one of the M-1 rounds and reduces through a log2(block)-deep __syncthreads tree.
+// B200 design: FPS is a latency chain, so everything a round touches lives in registers --
+// each thread owns PPT points (x,y,z,temp = 4*PPT registers) -- and a round is
+//   PPT distance updates -> warp arg-max by two `redux.sync` (value, then tie-break key)
+//   -> one 8-byte record per warp in shared memory -> ONE __syncthreads
+//   -> every warp re-reduces the <=32 records redundantly (no second barrier; records are
+//      double-buffered by round parity) -> winner coordinates by a broadcast LDS from the
+//      shared-memory copy of the cloud.
+//
+// Exact tie rule: the reference thread t = k mod block scans k ascending
+// with strict '>', and its tournament keeps the left operand on ties, so among equal maxima
+// the winner minimises (bitrev_{log2 block}(k mod block), k), block = min(1024, 2^floor(log2 n))
+// (cuda_utils.h:10-14).  We reduce on the 64-bit key (ordered(dist), ~((bitrev << 22) | k)),
+// which reproduces that total order for any assignment of points to threads.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace captra {
+
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ unsigned tie_key(int k, int ref_mask, int ref_shift) {
+    const unsigned rev = __brev((unsigned)(k & ref_mask)) >> ref_shift;  // bitrev over log2(block) bits
+    return ~((rev << 22) | (unsigned)k);
+}
+
+template <int NT, int PPT>
+__global__ void __launch_bounds__(NT)
+fps_reg_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
+               float *__restrict__ temp, int *__restrict__ idxs, float *__restrict__ new_xyz) {
+    extern __shared__ float smem[];  // sx[n] sy[n] sz[n]
+    __shared__ uint2 rec[2][32];
+    constexpr int NW = NT / 32;
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *cloud = dataset + (size_t)b * n * 3;
+    float *tmp = temp + (size_t)b * n;
+    int *out = idxs + (size_t)b * m;
+    float *oxyz = new_xyz ? new_xyz + (size_t)b * m * 3 : nullptr;
+    float *sx = smem, *sy = smem + n, *sz = smem + 2 * n;
+    const int ref_mask = (1 << ref_bits) - 1;
+    const int ref_shift = ref_bits ? 32 - ref_bits : 31;  // n == 1: mask 0, key bits 0
+
+    for (int e = tid; e < n * 3; e += NT) {
+        const int pt = e / 3, comp = e - pt * 3;
+        smem[comp * n + pt] = __ldg(cloud + e);
+    }
+    __syncthreads();
+
+    float x[PPT], y[PPT], z[PPT], t[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int k = tid + j * NT;
+        const bool ok = k < n;
+        x[j] = ok ? sx[k] : 0.f; y[j] = ok ? sy[k] : 0.f; z[j] = ok ? sz[k] : 0.f;
+        t[j] = ok ? tmp[k] : -INFINITY;  // never wins, never ties a real point
+    }
+
+    int old = 0;
+    float ox = sx[0], oy = sy[0], oz = sz[0];
+    if (tid == 0) {
+        out[0] = 0;
+        if (oxyz) { oxyz[0] = ox; oxyz[1] = oy; oxyz[2] = oz; }
+    }
+
+    for (int r = 1; r < m; ++r) {
+        float tm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float d = sqdist_ref(x[j], y[j], z[j], ox, oy, oz);
+            t[j] = fminf(d, t[j]);
+            tm = fmaxf(tm, t[j]);
+        }
+        const unsigned um = ordered_bits(tm);
+        const unsigned wm = __reduce_max_sync(kFull, um);
+        unsigned tb = 0;
+        if (um == wm) {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j)
+                if (t[j] == tm) tb = max(tb, tie_key(tid + j * NT, ref_mask, ref_shift));
+        }
+        const unsigned wt = __reduce_max_sync(kFull, tb);
+        unsigned bm, bt;
+        if (NW > 1) {
+            if (lane == 0) rec[r & 1][warp] = make_uint2(wm, wt);
+            __syncthreads();
+            const uint2 q = lane < NW ? rec[r & 1][lane] : make_uint2(0u, 0u);
+            bm = __reduce_max_sync(kFull, q.x);
+            bt = __reduce_max_sync(kFull, q.x == bm ? q.y : 0u);
+        } else {
+            bm = wm; bt = wt;
+        }
+        old = (int)((~bt) & 0x3fffffu);
+        ox = sx[old]; oy = sy[old]; oz = sz[old];
+        if (tid == 0) {
+            out[r] = old;
+            if (oxyz) { oxyz[r * 3 + 0] = ox; oxyz[r * 3 + 1] = oy; oxyz[r * 3 + 2] = oz; }
+        }
+    }
+
+    // the reference leaves its running min-distances in the caller's scratch
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int k = tid + j * NT;
+        if (k < n) tmp[k] = t[j];
+    }
+}
+
+// General-n path: running distances stay in the caller's temp (global/L2), coordinates are
+// re-read through the read-only path each round.  Same key, same order.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+fps_stream_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
+                  float *__restrict__ temp, int *__restrict__ idxs, float *__restrict__ new_xyz) {
+    __shared__ uint2 rec[2][32];
+    constexpr int NW = NT / 32;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *cloud = dataset + (size_t)b * n * 3;
+    float *tmp = temp + (size_t)b * n;
+    int *out = idxs + (size_t)b * m;
+    float *oxyz = new_xyz ? new_xyz + (size_t)b * m * 3 : nullptr;
+    const int ref_mask = (1 << ref_bits) - 1;
+    const int ref_shift = ref_bits ? 32 - ref_bits : 31;
+
+    int old = 0;
+    float ox = __ldg(cloud + 0), oy = __ldg(cloud + 1), oz = __ldg(cloud + 2);
+    if (tid == 0) {
+        out[0] = 0;
+        if (oxyz) { oxyz[0] = ox; oxyz[1] = oy; oxyz[2] = oz; }
+    }
+    for (int r = 1; r < m; ++r) {
+        unsigned um = 0, tb = 0;
+        for (int k = tid; k < n; k += NT) {
+            const float d = sqdist_ref(__ldg(cloud + k * 3 + 0), __ldg(cloud + k * 3 + 1),
+                                       __ldg(cloud + k * 3 + 2), ox, oy, oz);
+            const float d2 = fminf(d, tmp[k]);
+            tmp[k] = d2;
+            const unsigned u = ordered_bits(d2);
+            const unsigned key = tie_key(k, ref_mask, ref_shift);
+            if (u > um || (u == um && key > tb)) { um = u; tb = key; }
+        }
+        const unsigned wm = __reduce_max_sync(kFull, um);
+        const unsigned wt = __reduce_max_sync(kFull, um == wm ? tb : 0u);
+        if (lane == 0) rec[r & 1][warp] = make_uint2(wm, wt);
+        __syncthreads();
+        const uint2 q = lane < NW ? rec[r & 1][lane] : make_uint2(0u, 0u);
+        const unsigned bm = __reduce_max_sync(kFull, q.x);
+        const unsigned bt = __reduce_max_sync(kFull, q.x == bm ? q.y : 0u);
+        old = (int)((~bt) & 0x3fffffu);
+        ox = __ldg(cloud + old * 3 + 0); oy = __ldg(cloud + old * 3 + 1); oz = __ldg(cloud + old * 3 + 2);
+        if (tid == 0) {
+            out[r] = old;
+            if (oxyz) { oxyz[r * 3 + 0] = ox; oxyz[r * 3 + 1] = oy; oxyz[r * 3 + 2] = oz; }
+        }
+    }
+}
+
+template <int NT, int PPT>
+static int launch_fps_reg(int b, int n, int m, int ref_bits, const float *dataset, float *temp,
+                          int *idxs, float *new_xyz, cudaStream_t stream) {
+    auto kern = fps_reg_kernel<NT, PPT>;
+    const size_t smem = sizeof(float) * 3 * (size_t)n;
+    if (smem > 48 * 1024)
+        CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<b, NT, smem, stream>>>(n, m, ref_bits, dataset, temp, idxs, new_xyz);
+    CAPTRA_CHECK_LAUNCH("furthest_point_sampling");
+    return CAPTRA_OK;
+}
+
+}  // namespace captra
+
+using namespace captra;
+
+extern "C" int captra_fps_gather(int b, int n, int m, const float *dataset, float *temp,
+                                 int *idxs, float *new_xyz, captra_stream_t stream) {
+    CAPTRA_REQUIRE(b >= 0 && n >= 0 && m >= 0, "fps: negative size");
+    if (b == 0 || m <= 0) return CAPTRA_OK;  // sampling_gpu.cu:101 `if (m <= 0) return`
+    CAPTRA_REQUIRE(n >= 1, "fps: empty cloud with m > 0");
+    CAPTRA_REQUIRE(n < (1 << 22), "fps: n=%d exceeds the 2^22 key width", n);
+    CAPTRA_REQUIRE(dataset && temp && idxs, "fps: null pointer");
+    // block = min(1024, 2^floor(log2 n)) (cuda_utils.h:10-14); exact integer log2 here -- the
+    // reference's log()/log() quotient evaluates to the same integer for every n < 2^22
+    // (checked exhaustively in tests/test_oracle.py).
+    int ref_bits = 0;
+    while ((2 << ref_bits) <= n && ref_bits < 10) ++ref_bits;
+    cudaStream_t s = as_stream(stream);
+    if (n <= 128) return launch_fps_reg<32, 4>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+    if (n <= 512) return launch_fps_reg<128, 4>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+    if (n <= 1024) return launch_fps_reg<256, 4>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+    if (n <= 2048) return launch_fps_reg<256, 8>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+    if (n <= 4096) return launch_fps_reg<512, 8>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+    if (n <= 8192) return launch_fps_reg<1024, 8>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+    fps_stream_kernel<1024><<<b, 1024, 0, s>>>(n, m, ref_bits, dataset, temp, idxs, new_xyz);
+    CAPTRA_CHECK_LAUNCH("furthest_point_sampling(stream)");
+    return CAPTRA_OK;
+}
+
+extern "C" int furthest_point_sampling_kernel_launcher(int b, int n, int m, const float *dataset,
+                                                       float *temp, int *idxs,
+                                                       captra_stream_t stream) {
+    return captra_fps_gather(b, n, m, dataset, temp, idxs, nullptr, stream);
+}

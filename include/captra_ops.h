@@ -1,0 +1,185 @@
+/*
+ * captra_ops.h -- C ABI of libcaptra_ops.so, the B200-native (sm_100a) replacement for the
+ * launcher layer of CAPTRA's `pointnet2_cuda` extension plus the device-side pose fit.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless the
+ *     name ends in `_host`; `stream` is a cudaStream_t passed as void*;
+ *   - the caller allocates every output (same ownership as the reference,
+ *     pointnet2_utils.py:26-27,58,98-99,130-131,167,213,261);
+ *   - launches are asynchronous on `stream`, no internal sync, no global state, re-entrant;
+ *   - return value: CAPTRA_OK, or an error code -- the reference launchers print and
+ *     exit(-1) on a CUDA error (e.g. sampling_gpu.cu:248-252); we return the code and let the
+ *     binding raise.  captra_last_error() gives a thread-local message.
+ *
+ * Citations are into /root/reference/network/models/pointnet_lib/src/ (the FFI a reference
+ * maintainer would re-bind).
+ */
+#ifndef CAPTRA_OPS_H_
+#define CAPTRA_OPS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAPTRA_OK 0
+#define CAPTRA_ERR_INVALID_ARG 1
+#define CAPTRA_ERR_CUDA 2
+#define CAPTRA_ERR_UNSUPPORTED 3
+
+typedef void *captra_stream_t; /* cudaStream_t */
+
+const char *captra_last_error(void);
+int captra_abi_version(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+int64_t captra_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Drop-in launchers: same names, argument order and meaning as the reference's
+ *    *_kernel_launcher_fast functions; only the return type changes (void -> int status).
+ * ---------------------------------------------------------------------------------------- */
+
+/* ball_query_gpu.cu:48-49 (positional order is new_xyz, xyz -- ball_query_gpu.h:12 swaps the
+ * names).  new_xyz [B,M,3], xyz [B,N,3] -> idx [B,M,nsample] int32; rows of empty balls are
+ * left untouched (caller zeroes, pointnet2_utils.py:261). */
+int ball_query_kernel_launcher_fast(int b, int n, int m, float radius, int nsample,
+                                    const float *new_xyz, const float *xyz, int *idx,
+                                    captra_stream_t stream);
+
+/* group_points_gpu.h:13-14.  points [B,C,N], idx [B,npoints,nsample] -> out [B,C,npoints,nsample] */
+int group_points_kernel_launcher_fast(int b, int c, int n, int npoints, int nsample,
+                                      const float *points, const int *idx, float *out,
+                                      captra_stream_t stream);
+/* group_points_gpu.h:19-20.  grad_points [B,C,N] must be zeroed by the caller (:231) */
+int group_points_grad_kernel_launcher_fast(int b, int c, int n, int npoints, int nsample,
+                                           const float *grad_out, const int *idx,
+                                           float *grad_points, captra_stream_t stream);
+
+/* sampling_gpu.h:12-13.  points [B,C,N], idx [B,npoints] -> out [B,C,npoints] */
+int gather_points_kernel_launcher_fast(int b, int c, int n, int npoints, const float *points,
+                                       const int *idx, float *out, captra_stream_t stream);
+/* sampling_gpu.h:19-20 */
+int gather_points_grad_kernel_launcher_fast(int b, int c, int n, int npoints,
+                                            const float *grad_out, const int *idx,
+                                            float *grad_points, captra_stream_t stream);
+
+/* sampling_gpu.h:26-27.  dataset [B,N,3], temp [B,N] (caller pre-fills 1e10; read at entry and
+ * written back at exit exactly like the reference's in-place scratch) -> idxs [B,M] int32.
+ * Tie rule of the reference's shared-memory tournament is reproduced exactly
+ * (sampling_gpu.cu:86-91,119-203). */
+int furthest_point_sampling_kernel_launcher(int b, int n, int m, const float *dataset,
+                                            float *temp, int *idxs, captra_stream_t stream);
+
+/* interpolate_gpu.h:13-14.  unknown [B,n,3], known [B,m,3] -> dist2 [B,n,3] (SQUARED), idx [B,n,3] */
+int three_nn_kernel_launcher_fast(int b, int n, int m, const float *unknown,
+                                  const float *known, float *dist2, int *idx,
+                                  captra_stream_t stream);
+/* interpolate_gpu.h:19-20 (k <= 200 as in the reference, interpolate_gpu.cu:30) */
+int knn_kernel_launcher_fast(int b, int n, int m, int k, const float *unknown,
+                             const float *known, float *dist2, int *idx,
+                             captra_stream_t stream);
+/* interpolate_gpu.h:26-27.  points [B,C,m], idx/weight [B,n,3] -> out [B,C,n] */
+int three_interpolate_kernel_launcher_fast(int b, int c, int m, int n, const float *points,
+                                           const int *idx, const float *weight, float *out,
+                                           captra_stream_t stream);
+/* interpolate_gpu.h:33-34.  NOTE (b,c,n,m) order, unlike the forward's (b,c,m,n). */
+int three_interpolate_grad_kernel_launcher_fast(int b, int c, int n, int m,
+                                                const float *grad_out, const int *idx,
+                                                const float *weight, float *grad_points,
+                                                captra_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Fused entry points used by the host-side mirror of network/models/pointnet_utils.py.
+ *    Same per-element arithmetic as the ops above; they only remove HBM round trips.
+ * ---------------------------------------------------------------------------------------- */
+
+/* One scan of xyz answers up to CAPTRA_MAX_RADII ball queries that share the centroids
+ * (the MSG loop of pointnet_utils.py:228-233).  idx_r has nsample_r columns. */
+#define CAPTRA_MAX_RADII 4
+int captra_ball_query_multi(int b, int n, int m, int nradii, const float *radii_host,
+                            const int *nsamples_host, const float *new_xyz, const float *xyz,
+                            int *const *idx_host_ptrs, captra_stream_t stream);
+
+/* FPS + the gather that always follows it (pointnet_utils.py:225-226): additionally writes
+ * new_xyz [B,M,3] = dataset[b, idxs[b,:], :].  new_xyz may be NULL. */
+int captra_fps_gather(int b, int n, int m, const float *dataset, float *temp, int *idxs,
+                      float *new_xyz, captra_stream_t stream);
+
+/* three_nn + inverse-distance weights (pointnet_utils.py:284-287) + three_interpolate:
+ * out[., i] = sum_j w_j * points[., idx_j].  idx and weight [B,n,3] are required scratch /
+ * outputs; dist (the sqrt'ed distance ThreeNN returns, pointnet2_utils.py:134) may be NULL.
+ * point_major == 0: reference layout, points [B,C,m] -> out [B,C,n].
+ * point_major == 1: points [B,m,C] -> out row (b*n+i) at out + row*out_row_stride +
+ *                   out_col_offset (lets the caller write straight into a concat buffer). */
+int captra_three_nn_interpolate(int b, int c, int n, int m, const float *unknown,
+                                const float *known, const float *points, float *out,
+                                float *dist, int *idx, float *weight, int point_major,
+                                int64_t out_row_stride, int out_col_offset,
+                                captra_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Shared per-point MLPs (pointnet_utils.py:242-246, :296-298, :337-341; backbones.py:68).
+ *    Weights are passed pre-folded (conv bias + eval-mode BatchNorm -> W', b'), row-major
+ *    W'[cout][cin], fp32.
+ * ---------------------------------------------------------------------------------------- */
+#define CAPTRA_MAX_MLP_LAYERS 4
+
+typedef struct {
+    int nlayers;                          /* 1..CAPTRA_MAX_MLP_LAYERS */
+    int cin;                              /* input channels of layer 0 */
+    int cout[CAPTRA_MAX_MLP_LAYERS];      /* output channels per layer */
+    const float *w[CAPTRA_MAX_MLP_LAYERS];/* device, [cout_l][cin_l] */
+    const float *bias[CAPTRA_MAX_MLP_LAYERS]; /* device, [cout_l] */
+    int relu_last;                        /* apply ReLU after the last layer */
+} captra_mlp_desc;
+
+/* Fused set-abstraction scale (pointnet_utils.py:233-246): for every centroid s and sample k
+ *   row = [ feats[b, :, idx[b,s,k]] (cfeat ch) , xyz[b, idx[b,s,k], :] - new_xyz[b,s,:] (3 ch) ]
+ * -> MLP (ReLU after every layer) -> max over k -> out[b, out_ch_offset + c, s].
+ * feats is POINT-major [B,N,cfeat] (may be NULL when cfeat==0); out is [B, out_ch_total, S].
+ * impl: 0 = fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel. */
+int captra_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz,
+                      const float *new_xyz, const float *feats, const int *idx,
+                      const captra_mlp_desc *mlp, float *out, int out_ch_total,
+                      int out_ch_offset, int impl, captra_stream_t stream);
+
+/* Pointwise MLP on rows: x [rows, cin] row-major (point-major) -> y [rows, cout_last].
+ * If group > 0 a max over each consecutive `group` rows is taken (group-all SA,
+ * pointnet_utils.py:337-343) and y is [rows/group, cout_last]. */
+int captra_point_mlp(int64_t rows, const float *x, const captra_mlp_desc *mlp, float *y,
+                     int group, int impl, captra_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Pose fit (pose_utils/procrustes.py, pose_utils/pose_fit.py) -- Python in the reference,
+ *    with torch.svd on the CPU (procrustes.py:27-30,170-174); here on the device.
+ * ---------------------------------------------------------------------------------------- */
+
+/* R = U diag(1,1,det(U V^T)) V^T for count 3x3 matrices M (row-major) -- procrustes.py:30-54 */
+int captra_procrustes_rot3(int64_t count, const float *M, float *R, captra_stream_t stream);
+/* 2x2 variant with the orthogonality check / identity fallback -- procrustes.py:174-204 */
+int captra_procrustes_rot2(int64_t count, const float *M, float *R, captra_stream_t stream);
+
+/* Fused part_fit_st_no_ransac (pose_fit.py:38-53 -> procrustes.py:132-164):
+ *   mask[b,p,i] = (labels[b,i] == p); valid = sum(mask) > 3 and outputs finite
+ *   (optional sym refinement R <- R*Ry via the 2-D fit, procrustes.py:147-151,213-228)
+ *   scale       = sum w (R s_c).t_c / (sum w |R s_c|^2 + 1e-6)     (or given_scale)
+ *   translation = sum w (t - scale R s) / max(sum w, 1)
+ * source/target are addressed through element strides (in floats) so the reference's
+ * transposed views ([B,P,3,N].transpose(-1,-2), networks.py:227) need no copy:
+ *   src(b,p,i,c) = source[b*ssb + p*ssp + i*ssn + c*ssc].
+ * rotation [B,P,3,3] row-major or NULL (-> 3x3 Procrustes, procrustes.py:142-145).
+ * Outputs: scale [B,P], translation [B,P,3], valid [B,P] (uint8), rot_out [B,P,3,3] (the
+ * rotation actually used for s,t -- may be NULL). */
+int captra_part_fit_st(int b, int p, int n, const int64_t *labels, const float *source,
+                       int64_t ssb, int64_t ssp, int64_t ssn, int64_t ssc,
+                       const float *target, int64_t tsb, int64_t tsp, int64_t tsn,
+                       int64_t tsc, const float *rotation, const float *given_scale, int sym,
+                       float *scale, float *translation, uint8_t *valid, float *rot_out,
+                       captra_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPTRA_OPS_H_ */

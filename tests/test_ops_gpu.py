@@ -1,0 +1,195 @@
+"""GPU parity tests for the pointnet_lib ops, through the
+reference-shaped Python API -> C ABI -> sm_100a kernels.
+
+Bars: indices bit-exact; copies bit-exact; three_interpolate bit-exact (same FMA order);
+atomic-add adjoints to 1e-5 (summation order is unspecified in the reference too).
+Three-way check: product == oracle (CPU restatement) == reference CUDA kernels (oracle/_ref).
+"""
+import numpy as np
+import pytest
+import torch
+
+from captra_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+@pytest.fixture(scope="module")
+def futils(cuda):
+    from captra_b200.pointnet_lib import pointnet2_utils
+    return pointnet2_utils
+
+
+@pytest.fixture(scope="module")
+def refcu(cuda):
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    return ref_cuda
+
+
+CLOUDS = {
+    "surface4096": lambda: synthetic.batch_surface_box(3, 4096, seed=0)[0],
+    "uniform5000": lambda: synthetic.batch_uniform(2, 5000, seed=1),       # n not a power of two
+    "tiled4096": lambda: synthetic.batch_tiled(2, 4096, 1500, seed=2),     # exact duplicates
+    "small100": lambda: synthetic.batch_uniform(4, 100, seed=3),
+    "sa2_512": lambda: synthetic.batch_surface_box(4, 512, seed=4)[0],
+    "n1": lambda: synthetic.batch_uniform(2, 1, seed=5),
+    "n33": lambda: synthetic.batch_tiled(2, 33, 5, seed=6),
+}
+
+
+@pytest.mark.parametrize("name,m", [("surface4096", 512), ("uniform5000", 300), ("tiled4096", 2000),
+                                    ("small100", 100), ("sa2_512", 128), ("n1", 3), ("n33", 33)])
+def test_fps_bit_exact(name, m, futils, oracle, refcu, cuda):
+    pts = CLOUDS[name]()
+    want = oracle.furthest_point_sample(pts, m)
+    got = futils.furthest_point_sample(dev(pts, cuda), m)
+    assert got.dtype == torch.int32 and tuple(got.shape) == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)
+    ref = refcu.furthest_point_sample(dev(pts, cuda), m)
+    assert np.array_equal(ref.cpu().numpy(), want), "oracle disagrees with the reference kernel"
+
+
+def test_fps_large_n_stream_path_and_temp(oracle, refcu, cuda):
+    # crop FPS: up to 20480 points -> 4096 (data_utils.py:146-158); also checks the scratch
+    # `temp` the reference leaves behind
+    pts = synthetic.batch_surface_box(1, 20480, seed=7)[0]
+    from captra_b200 import pointnet2_cuda
+    x = dev(pts, cuda)
+    for n, m in ((20480, 1024), (9000, 500), (8192, 700)):
+        xs = x[:, :n].contiguous()
+        temp = torch.full((1, n), 1e10, device=cuda)
+        idx = torch.empty(1, m, dtype=torch.int32, device=cuda)
+        pointnet2_cuda.furthest_point_sampling_wrapper(1, n, m, xs, temp, idx)
+        want, wtemp = oracle.furthest_point_sample(pts[:, :n], m, return_temp=True)
+        assert np.array_equal(idx.cpu().numpy(), want)
+        assert np.array_equal(temp.cpu().numpy(), wtemp)
+    ridx, rtemp = refcu.furthest_point_sample(x[:, :9000].contiguous(), 500, return_temp=True)
+    want, wtemp = oracle.furthest_point_sample(pts[:, :9000], 500, return_temp=True)
+    assert np.array_equal(ridx.cpu().numpy(), want) and np.array_equal(rtemp.cpu().numpy(), wtemp)
+
+
+@pytest.mark.parametrize("name,m,radius,k", [
+    ("surface4096", 512, 0.05, 32), ("surface4096", 512, 0.1, 64), ("surface4096", 512, 0.2, 128),
+    ("sa2_512", 128, 0.2, 64), ("sa2_512", 128, 0.4, 128), ("uniform5000", 77, 0.15, 16),
+    ("tiled4096", 100, 0.1, 48), ("small100", 100, 0.3, 200), ("n1", 1, 1.0, 4)])
+def test_ball_query_bit_exact(name, m, radius, k, futils, oracle, refcu, cuda):
+    pts = CLOUDS[name]()
+    ctr = np.ascontiguousarray(pts[:, oracle.furthest_point_sample(pts, m)[0]])
+    ctr[0, 0] += 50.0  # one empty ball: row must stay zero
+    want = oracle.ball_query(radius, k, pts, ctr)
+    got = futils.ball_query(radius, k, dev(pts, cuda), dev(ctr, cuda))
+    assert got.dtype == torch.int32
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert (got[0, 0] == 0).all()
+    ref = refcu.ball_query(radius, k, dev(pts, cuda), dev(ctr, cuda))
+    assert np.array_equal(ref.cpu().numpy(), want), "oracle disagrees with the reference kernel"
+
+
+def test_ball_query_multi_radius_equals_single(oracle, cuda):
+    import ctypes
+    from captra_b200 import _lib
+    L = _lib.load()
+    pts = CLOUDS["surface4096"]()
+    ctr = np.ascontiguousarray(pts[:, :512])
+    x, c = dev(pts, cuda), dev(ctr, cuda)
+    radii, ks = [0.05, 0.1, 0.2], [32, 64, 128]
+    outs = [torch.zeros(3, 512, k, dtype=torch.int32, device=cuda) for k in ks]
+    ra = (ctypes.c_float * 3)(*radii)
+    ka = (ctypes.c_int * 3)(*ks)
+    pa = (ctypes.c_void_p * 3)(*[o.data_ptr() for o in outs])
+    _lib.check(L.captra_ball_query_multi(3, 4096, 512, 3, ra, ka, x.data_ptr(), c.data_ptr(), pa,
+                                         _lib.stream_ptr()), "ball_query_multi")
+    for r, k, o in zip(radii, ks, outs):
+        assert np.array_equal(o.cpu().numpy(), oracle.ball_query(r, k, pts, ctr))
+
+
+def test_group_gather_bit_exact(futils, oracle, refcu, cuda):
+    rng = np.random.default_rng(0)
+    for (B, C, N, M, K) in ((2, 6, 4096, 512, 32), (2, 323, 512, 128, 64), (1, 5, 301, 7, 3)):
+        feats = rng.normal(size=(B, C, N)).astype(np.float32)
+        idx = rng.integers(0, N, size=(B, M, K)).astype(np.int32)
+        want = oracle.grouping_operation(feats, idx)
+        got = futils.grouping_operation(dev(feats, cuda), dev(idx, cuda))
+        assert np.array_equal(got.cpu().numpy(), want)
+        assert np.array_equal(refcu.grouping_operation(dev(feats, cuda), dev(idx, cuda)).cpu().numpy(), want)
+        sidx = np.ascontiguousarray(idx[:, :, 0])
+        want = oracle.gather_operation(feats, sidx)
+        got = futils.gather_operation(dev(feats, cuda), dev(sidx, cuda))
+        assert np.array_equal(got.cpu().numpy(), want)
+        assert np.array_equal(refcu.gather_operation(dev(feats, cuda), dev(sidx, cuda)).cpu().numpy(), want)
+
+
+def test_three_nn_interpolate_bit_exact(futils, oracle, refcu, cuda):
+    for (B, n, m, C, seed) in ((2, 4096, 512, 128, 0), (2, 512, 128, 256, 1), (1, 77, 2, 5, 2), (1, 300, 3000, 4, 3)):
+        unk = synthetic.batch_uniform(B, n, seed=seed)
+        kn = synthetic.batch_uniform(B, m, seed=seed + 10)
+        kn[:, 1:3] = kn[:, 0:1] if m > 3 else kn[:, 1:3]  # duplicated known points: tie order
+        wd, wi = oracle.three_nn(unk, kn, sqrt=False)
+        gd, gi = futils.three_nn(dev(unk, cuda), dev(kn, cuda))
+        assert np.array_equal(gi.cpu().numpy(), wi)
+        assert np.array_equal(gd.cpu().numpy(), np.sqrt(wd))
+        rd, ri = refcu.three_nn(dev(unk, cuda), dev(kn, cuda))
+        assert np.array_equal(ri.cpu().numpy(), wi) and np.array_equal(rd.cpu().numpy(), wd)
+        feats = np.random.default_rng(seed).normal(size=(B, C, m)).astype(np.float32)
+        w = oracle.interp_weights(np.sqrt(wd)) if m >= 3 else np.full((B, n, 3), 1 / 3, np.float32)
+        want = oracle.three_interpolate(feats, wi, w)
+        got = futils.three_interpolate(dev(feats, cuda), dev(wi, cuda), dev(w, cuda))
+        assert np.array_equal(got.cpu().numpy(), want)
+        ref = refcu.three_interpolate(dev(feats, cuda), dev(wi, cuda), dev(w, cuda))
+        assert np.array_equal(ref.cpu().numpy(), want), "oracle disagrees with the reference kernel"
+
+
+def test_knn_bit_exact(futils, oracle, refcu, cuda):
+    unk = synthetic.batch_uniform(2, 333, seed=0)
+    kn = synthetic.batch_uniform(2, 500, seed=1)
+    for k in (1, 3, 16, 200):
+        wd, wi = oracle.knn(k, unk, kn, sqrt=False)
+        gd, gi = futils.knn(k, dev(unk, cuda), dev(kn, cuda))
+        assert np.array_equal(gi.cpu().numpy(), wi)
+        assert np.array_equal(gd.cpu().numpy(), np.sqrt(wd))
+        rd, ri = refcu.knn(k, dev(unk, cuda), dev(kn, cuda))
+        assert np.array_equal(ri.cpu().numpy(), wi) and np.array_equal(rd.cpu().numpy(), wd)
+
+
+def test_backward_ops(futils, oracle, refcu, cuda):
+    rng = np.random.default_rng(0)
+    B, C, N, M, K, n = 2, 16, 512, 64, 8, 700
+    x = dev(rng.normal(size=(B, C, N)).astype(np.float32), cuda).requires_grad_(True)
+    idx = rng.integers(0, N, size=(B, M, K)).astype(np.int32)
+    g = rng.normal(size=(B, C, M, K)).astype(np.float32)
+    futils.grouping_operation(x, dev(idx, cuda)).backward(dev(g, cuda))
+    np.testing.assert_allclose(x.grad.cpu().numpy(), oracle.grouping_operation_grad(g, idx, N), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(refcu.grouping_operation_grad(dev(g, cuda), dev(idx, cuda), N).cpu().numpy(),
+                               oracle.grouping_operation_grad(g, idx, N), rtol=1e-5, atol=1e-5)
+    x.grad = None
+    sidx = np.ascontiguousarray(idx[:, :, 0])
+    g2 = rng.normal(size=(B, C, M)).astype(np.float32)
+    futils.gather_operation(x, dev(sidx, cuda)).backward(dev(g2, cuda))
+    np.testing.assert_allclose(x.grad.cpu().numpy(), oracle.gather_operation_grad(g2, sidx, N), rtol=1e-5, atol=1e-5)
+    x.grad = None
+    idx3 = rng.integers(0, N, size=(B, n, 3)).astype(np.int32)
+    w = rng.random((B, n, 3)).astype(np.float32)
+    g3 = rng.normal(size=(B, C, n)).astype(np.float32)
+    futils.three_interpolate(x, dev(idx3, cuda), dev(w, cuda)).backward(dev(g3, cuda))
+    np.testing.assert_allclose(x.grad.cpu().numpy(), oracle.three_interpolate_grad(g3, idx3, w, N), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(refcu.three_interpolate_grad(dev(g3, cuda), dev(idx3, cuda), dev(w, cuda), N).cpu().numpy(),
+                               oracle.three_interpolate_grad(g3, idx3, w, N), rtol=1e-5, atol=1e-5)
+
+
+def test_rejects_cpu_tensors_and_missing_lib(futils, cuda):
+    from captra_b200._lib import CaptraError
+    with pytest.raises(CaptraError):
+        futils.furthest_point_sample(torch.zeros(1, 10, 3), 2)
+
+
+def test_empty_batch_and_zero_sizes(futils, cuda):
+    assert futils.ball_query(0.1, 4, torch.zeros(0, 10, 3, device=cuda), torch.zeros(0, 2, 3, device=cuda)).shape == (0, 2, 4)
+    assert futils.furthest_point_sample(torch.zeros(0, 10, 3, device=cuda), 4).shape == (0, 4)
+    out = futils.grouping_operation(torch.zeros(2, 0, 10, device=cuda), torch.zeros(2, 3, 4, dtype=torch.int32, device=cuda))
+    assert out.shape == (2, 0, 3, 4)
