@@ -32,6 +32,9 @@ SIGNATURES = {
     "captra_ball_query_multi": [c_int] * 4 + [_P, _P, _P, _P, _P, _P],
     "captra_fps_gather": [c_int] * 3 + [_P, _P, _P, _P, _P],
     "captra_three_nn_interpolate": [c_int] * 4 + [_P] * 7 + [c_int, c_i64, c_int, _P],
+    "captra_procrustes_rot3": [c_i64, _P, _P, _P],
+    "captra_procrustes_rot2": [c_i64, _P, _P, _P],
+    "captra_part_fit_st": [c_int] * 3 + [_P, _P] + [_P] + [c_i64] * 4 + [_P] + [c_i64] * 4 + [_P, _P, c_int, _P, _P, _P, _P, _P],
 }
 OTHER_SYMBOLS = ["captra_last_error", "captra_abi_version", "captra_launch_count"]
 

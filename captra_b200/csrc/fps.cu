@@ -167,8 +167,9 @@ static int launch_fps_reg(int b, int n, int m, int ref_bits, const float *datase
                           int *idxs, float *new_xyz, cudaStream_t stream) {
     auto kern = fps_reg_kernel<NT, PPT>;
     const size_t smem = sizeof(float) * 3 * (size_t)n;
-    if (smem > 48 * 1024)
-        CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // static smem (the records) counts against the 48 KB default; opting in needs a value > 48 KB
+    if (smem + 1024 > 48 * 1024)
+        CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
     kern<<<b, NT, smem, stream>>>(n, m, ref_bits, dataset, temp, idxs, new_xyz);
     CAPTRA_CHECK_LAUNCH("furthest_point_sampling");
     return CAPTRA_OK;

@@ -162,7 +162,9 @@ int captra_procrustes_rot3(int64_t count, const float *M, float *R, captra_strea
 int captra_procrustes_rot2(int64_t count, const float *M, float *R, captra_stream_t stream);
 
 /* Fused part_fit_st_no_ransac (pose_fit.py:38-53 -> procrustes.py:132-164):
- *   mask[b,p,i] = (labels[b,i] == p); valid = sum(mask) > 3 and outputs finite
+ *   mask[b,p,i] = (labels[b,i] == p) (labels int64 [B,N]), or -- when labels is NULL -- the
+ *   binary float mask [B,P,N] given in `mask` (exactly one of the two must be non-NULL);
+ *   valid = sum(mask) > 3 and outputs finite
  *   (optional sym refinement R <- R*Ry via the 2-D fit, procrustes.py:147-151,213-228)
  *   scale       = sum w (R s_c).t_c / (sum w |R s_c|^2 + 1e-6)     (or given_scale)
  *   translation = sum w (t - scale R s) / max(sum w, 1)
@@ -172,11 +174,11 @@ int captra_procrustes_rot2(int64_t count, const float *M, float *R, captra_strea
  * rotation [B,P,3,3] row-major or NULL (-> 3x3 Procrustes, procrustes.py:142-145).
  * Outputs: scale [B,P], translation [B,P,3], valid [B,P] (uint8), rot_out [B,P,3,3] (the
  * rotation actually used for s,t -- may be NULL). */
-int captra_part_fit_st(int b, int p, int n, const int64_t *labels, const float *source,
-                       int64_t ssb, int64_t ssp, int64_t ssn, int64_t ssc,
-                       const float *target, int64_t tsb, int64_t tsp, int64_t tsn,
-                       int64_t tsc, const float *rotation, const float *given_scale, int sym,
-                       float *scale, float *translation, uint8_t *valid, float *rot_out,
+int captra_part_fit_st(int b, int p, int n, const int64_t *labels, const float *mask,
+                       const float *source, int64_t ssb, int64_t ssp, int64_t ssn, int64_t ssc,
+                       const float *target, int64_t tsb, int64_t tsp, int64_t tsn, int64_t tsc,
+                       const float *rotation, const float *given_scale, int sym, float *scale,
+                       float *translation, uint8_t *valid, float *rot_out,
                        captra_stream_t stream);
 
 #ifdef __cplusplus

@@ -103,7 +103,7 @@ def test_ball_query_multi_radius_equals_single(oracle, cuda):
     ra = (ctypes.c_float * 3)(*radii)
     ka = (ctypes.c_int * 3)(*ks)
     pa = (ctypes.c_void_p * 3)(*[o.data_ptr() for o in outs])
-    _lib.check(L.captra_ball_query_multi(3, 4096, 512, 3, ra, ka, x.data_ptr(), c.data_ptr(), pa,
+    _lib.check(L.captra_ball_query_multi(3, 4096, 512, 3, ra, ka, c.data_ptr(), x.data_ptr(), pa,
                                          _lib.stream_ptr()), "ball_query_multi")
     for r, k, o in zip(radii, ks, outs):
         assert np.array_equal(o.cpu().numpy(), oracle.ball_query(r, k, pts, ctr))
