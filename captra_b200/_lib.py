@@ -32,11 +32,14 @@ SIGNATURES = {
     "captra_ball_query_multi": [c_int] * 4 + [_P, _P, _P, _P, _P, _P],
     "captra_fps_gather": [c_int] * 3 + [_P, _P, _P, _P, _P],
     "captra_three_nn_interpolate": [c_int] * 4 + [_P] * 7 + [c_int, c_i64, c_int, _P],
+    "captra_mlp_pack": [_P, c_int, _P, _P],
+    "captra_sa_mlp_max": [c_int] * 5 + [_P] * 7 + [c_i64, c_int, c_int, _P],
+    "captra_point_mlp": [c_i64, _P, c_i64, c_int, _P, c_i64, c_int, c_int, _P, _P, _P, c_i64, c_int, c_int, c_int, _P],
     "captra_procrustes_rot3": [c_i64, _P, _P, _P],
     "captra_procrustes_rot2": [c_i64, _P, _P, _P],
     "captra_part_fit_st": [c_int] * 3 + [_P, _P] + [_P] + [c_i64] * 4 + [_P] + [c_i64] * 4 + [_P, _P, c_int, _P, _P, _P, _P, _P],
 }
-OTHER_SYMBOLS = ["captra_last_error", "captra_abi_version", "captra_launch_count"]
+OTHER_SYMBOLS = ["captra_last_error", "captra_abi_version", "captra_launch_count", "captra_mlp_pack_bytes"]
 
 
 class CaptraError(RuntimeError):
@@ -60,6 +63,8 @@ def load():
     lib.captra_last_error.restype = ctypes.c_char_p
     lib.captra_abi_version.restype = c_int
     lib.captra_launch_count.restype = c_i64
+    lib.captra_mlp_pack_bytes.restype = c_i64
+    lib.captra_mlp_pack_bytes.argtypes = [_P, c_int]
     _lib = lib
     return lib
 
@@ -67,6 +72,26 @@ def load():
 def check(status, what):
     if status != 0:
         raise CaptraError("%s failed (status %d): %s" % (what, status, load().captra_last_error().decode()))
+
+
+# --- optional per-call device timing (bench.py's roofline pass) ---------------------------------
+# When PROFILE is a list, call() brackets every C-ABI call with CUDA events on the current stream
+# and appends (tag, start_event, end_event).  Off (None) in normal operation: zero overhead.
+PROFILE = None
+
+
+def call(tag, fn, *args, device=None):
+    """Invoke a C-ABI entry point, raise on a non-zero status, optionally time it."""
+    if PROFILE is None:
+        status = fn(*args)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(device))
+        status = fn(*args)
+        e1.record(torch.cuda.current_stream(device))
+        PROFILE.append((tag, e0, e1))
+    if status != 0:
+        raise CaptraError("%s failed (status %d): %s" % (tag, status, load().captra_last_error().decode()))
 
 
 def launch_count():

@@ -1,0 +1,66 @@
+// mlp_api.cu -- C ABI of the fused per-point MLP kernels; dispatches on `impl`
+// (0: fp32 CUDA cores, mlp_simt.cu; 1: tcgen05 3xTF32, mlp_tc.cu).
+#include "mlp_common.cuh"
+
+namespace captra {
+int simt_pack(const captra_mlp_desc *d, void *packed, cudaStream_t stream);
+int simt_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const float *new_xyz,
+                    const float *feats, const int *idx, const captra_mlp_desc *d, const void *packed,
+                    float *out, int64_t ldo, int col_off, cudaStream_t stream);
+int simt_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB,
+                   int cb, int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
+                   int col_off, int group, cudaStream_t stream);
+}  // namespace captra
+
+using namespace captra;
+
+extern "C" int64_t captra_mlp_pack_bytes(const captra_mlp_desc *d, int impl) {
+    if (check_desc(d, "mlp_pack_bytes") != CAPTRA_OK) return -1;
+    if (impl == 0) return (int64_t)(simt_layout(*d).total_floats * sizeof(float));
+    set_error("mlp_pack_bytes: impl %d not available", impl);
+    return -1;
+}
+
+extern "C" int captra_mlp_pack(const captra_mlp_desc *d, int impl, void *packed, captra_stream_t stream) {
+    int rc = check_desc(d, "mlp_pack");
+    if (rc) return rc;
+    CAPTRA_REQUIRE(packed && (reinterpret_cast<uintptr_t>(packed) & 15) == 0, "mlp_pack: packed buffer must be 16-byte aligned");
+    for (int l = 0; l < d->nlayers; ++l) CAPTRA_REQUIRE(d->w[l], "mlp_pack: null weights for layer %d", l);
+    if (impl == 0) return simt_pack(d, packed, as_stream(stream));
+    set_error("mlp_pack: impl %d not available", impl);
+    return CAPTRA_ERR_UNSUPPORTED;
+}
+
+extern "C" int captra_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz,
+                                 const float *new_xyz, const float *feats, const int *idx,
+                                 const captra_mlp_desc *d, const void *packed, float *out,
+                                 int64_t ldo, int col_off, int impl, captra_stream_t stream) {
+    int rc = check_desc(d, "sa_mlp_max");
+    if (rc) return rc;
+    CAPTRA_REQUIRE(b >= 0 && n >= 1 && s >= 0 && k >= 1 && cfeat >= 0, "sa_mlp_max: bad sizes");
+    CAPTRA_REQUIRE(d->cin == cfeat + 3, "sa_mlp_max: mlp cin=%d but cfeat+3=%d", d->cin, cfeat + 3);
+    if (b == 0 || s == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(xyz && new_xyz && idx && packed && out && (feats || cfeat == 0), "sa_mlp_max: null pointer");
+    CAPTRA_REQUIRE((int64_t)b * n < (1LL << 31), "sa_mlp_max: b*n overflows int");
+    if (impl == 0)
+        return simt_sa_mlp_max(b, n, s, k, cfeat, xyz, new_xyz, feats, idx, d, packed, out, ldo, col_off, as_stream(stream));
+    set_error("sa_mlp_max: impl %d not available", impl);
+    return CAPTRA_ERR_UNSUPPORTED;
+}
+
+extern "C" int captra_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB,
+                                int64_t ldB, int cb, int bcast_rows, const captra_mlp_desc *d,
+                                const void *packed, float *y, int64_t ldy, int col_off, int group,
+                                int impl, captra_stream_t stream) {
+    int rc = check_desc(d, "point_mlp");
+    if (rc) return rc;
+    CAPTRA_REQUIRE(rows >= 0 && ca >= 0 && cb >= 0 && group >= 0 && bcast_rows >= 0, "point_mlp: bad sizes");
+    CAPTRA_REQUIRE(d->cin == ca + cb, "point_mlp: mlp cin=%d but ca+cb=%d", d->cin, ca + cb);
+    CAPTRA_REQUIRE(group == 0 || rows % group == 0, "point_mlp: rows %lld not a multiple of group %d", (long long)rows, group);
+    if (rows == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(packed && y && (segA || ca == 0) && (segB || cb == 0), "point_mlp: null pointer");
+    if (impl == 0)
+        return simt_point_mlp(rows, segA, ldA, ca, segB, ldB, cb, bcast_rows, d, packed, y, ldy, col_off, group, as_stream(stream));
+    set_error("point_mlp: impl %d not available", impl);
+    return CAPTRA_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,53 @@
+"""Thin Python fronts for the fused entry points of include/captra_ops.h section 2.
+Point-major tensors in, point-major tensors out; every call is one or two kernel launches."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_f32, _i32 = torch.float32, torch.int32
+
+
+def fps_gather(xyz, npoint):
+    """xyz [B,N,3] -> (idx [B,npoint] int32, new_xyz [B,npoint,3]); pointnet_utils.py:225-226."""
+    B, N, _ = xyz.shape
+    idx = torch.empty(B, npoint, dtype=_i32, device=xyz.device)
+    new_xyz = torch.empty(B, npoint, 3, dtype=_f32, device=xyz.device)
+    temp = torch.full((B, N), 1e10, dtype=_f32, device=xyz.device)
+    _lib.call("fps_gather[N=%d,M=%d]" % (N, npoint), _lib.load().captra_fps_gather, B, N, npoint,
+              _lib.ptr(xyz, _f32, "xyz"), temp.data_ptr(), idx.data_ptr(), new_xyz.data_ptr(),
+              _lib.stream_ptr(xyz.device), device=xyz.device)
+    return idx, new_xyz
+
+
+def ball_query_multi(radii, nsamples, xyz, new_xyz):
+    """One scan for all radii of an MSG layer (pointnet_utils.py:228-233) -> list of idx [B,S,K_r]."""
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    nr = len(radii)
+    outs = [torch.zeros(B, S, k, dtype=_i32, device=xyz.device) for k in nsamples]
+    ra = (ctypes.c_float * nr)(*[float(r) for r in radii])
+    ka = (ctypes.c_int * nr)(*[int(k) for k in nsamples])
+    pa = (ctypes.c_void_p * nr)(*[o.data_ptr() for o in outs])
+    _lib.call("ball_query_multi[N=%d,S=%d,K=%s]" % (N, S, "/".join(map(str, nsamples))),
+              _lib.load().captra_ball_query_multi, B, N, S, nr, ra, ka, _lib.ptr(new_xyz, _f32, "new_xyz"),
+              _lib.ptr(xyz, _f32, "xyz"), pa, _lib.stream_ptr(xyz.device), device=xyz.device)
+    return outs
+
+
+def three_nn_interpolate_pm(unknown, known, feats_pm, out=None, col_off=0):
+    """unknown [B,n,3], known [B,m,3], feats_pm [B,m,C] -> out [B,n,C] (or into out[..., col_off:]);
+    3-NN + inverse-distance weights + interpolation (pointnet_utils.py:284-289)."""
+    B, n, _ = unknown.shape
+    m, C = known.shape[1], feats_pm.shape[2]
+    dev = unknown.device
+    idx = torch.empty(B, n, 3, dtype=_i32, device=dev)
+    w = torch.empty(B, n, 3, dtype=_f32, device=dev)
+    if out is None:
+        out = torch.empty(B, n, C, dtype=_f32, device=dev)
+    _lib.call("three_nn_interpolate[n=%d,m=%d,C=%d]" % (n, m, C), _lib.load().captra_three_nn_interpolate,
+              B, C, n, m, _lib.ptr(unknown, _f32, "unknown"), _lib.ptr(known, _f32, "known"),
+        _lib.ptr(feats_pm, _f32, "feats"), _lib.ptr(out, _f32, "out"), None, idx.data_ptr(), w.data_ptr(),
+        1, out.shape[-1], col_off, _lib.stream_ptr(dev), device=dev)
+    return out

@@ -1,0 +1,115 @@
+"""Host side of the fused per-point MLP kernels (csrc/mlp_simt.cu, csrc/mlp_tc.cu).
+
+`PackedMLP` folds conv bias + eval-mode BatchNorm into (W', b'), hands them to captra_mlp_pack
+once, and exposes the two execution calls of include/captra_ops.h section 3.  Internal tensors
+are POINT-major ([rows, channels], channels contiguous): that is the natural A-operand layout
+ and makes every gather a contiguous row read.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+
+MAX_LAYERS = 4
+# 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel.  CAPTRA_MLP_IMPL overrides.
+DEFAULT_IMPL = int(os.environ.get("CAPTRA_MLP_IMPL", "0"))
+
+
+class MlpDesc(ctypes.Structure):
+    """captra_mlp_desc (include/captra_ops.h)."""
+    _fields_ = [("nlayers", ctypes.c_int), ("cin", ctypes.c_int), ("cout", ctypes.c_int * MAX_LAYERS),
+                ("w", ctypes.c_void_p * MAX_LAYERS), ("bias", ctypes.c_void_p * MAX_LAYERS),
+                ("relu_last", ctypes.c_int)]
+
+
+def fold_conv_bn(conv, bn=None):
+    """(W [cout,cin], b [cout]) of conv (kernel size 1) followed by eval-mode BatchNorm:
+    y = gamma * (Wx + b - mean) / sqrt(var + eps) + beta."""
+    W = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).to(torch.float32)
+    b = conv.bias.detach().to(torch.float32) if conv.bias is not None else torch.zeros(conv.out_channels, device=W.device)
+    if bn is not None:
+        g = bn.weight.detach() if bn.weight is not None else torch.ones_like(bn.running_var)
+        beta = bn.bias.detach() if bn.bias is not None else torch.zeros_like(bn.running_var)
+        scale = g / torch.sqrt(bn.running_var.detach() + bn.eps)
+        W = W * scale[:, None]
+        b = (b - bn.running_mean.detach()) * scale + beta
+    return W.contiguous(), b.contiguous()
+
+
+class PackedMLP:
+    """A chain of up to 4 (linear + bias [+ ReLU]) layers with weights packed for one impl."""
+
+    def __init__(self, weights, biases, relu_last=True, impl=None):
+        assert 1 <= len(weights) <= MAX_LAYERS and len(weights) == len(biases)
+        self.impl = DEFAULT_IMPL if impl is None else impl
+        self.device = weights[0].device
+        if self.device.type != "cuda":
+            raise _lib.CaptraError("PackedMLP: weights must live on a CUDA device (no CPU path)")
+        self.cin = int(weights[0].shape[1])
+        self.couts = [int(w.shape[0]) for w in weights]
+        d = MlpDesc()
+        d.nlayers, d.cin, d.relu_last = len(weights), self.cin, 1 if relu_last else 0
+        keep = []
+        for l, (w, b) in enumerate(zip(weights, biases)):
+            w = w.detach().to(torch.float32).contiguous()
+            b = b.detach().to(torch.float32).contiguous()
+            assert w.shape[1] == (self.cin if l == 0 else self.couts[l - 1]), "layer %d: cin mismatch" % l
+            keep += [w, b]
+            d.cout[l], d.w[l], d.bias[l] = self.couts[l], w.data_ptr(), b.data_ptr()
+        self.desc = d
+        L = _lib.load()
+        nbytes = L.captra_mlp_pack_bytes(ctypes.byref(d), self.impl)
+        if nbytes < 0:
+            raise _lib.CaptraError("mlp_pack_bytes: " + L.captra_last_error().decode())
+        self.packed = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        _lib.check(L.captra_mlp_pack(ctypes.byref(d), self.impl, self.packed.data_ptr(),
+                                     _lib.stream_ptr(self.device)), "mlp_pack")
+        # the pack kernels read w/b asynchronously on the current stream; stream order keeps that
+        # safe as long as the tensors outlive the enqueue, which `keep` guarantees until here
+        torch.cuda.current_stream(self.device).synchronize()
+        for l in range(MAX_LAYERS):  # the execution calls never dereference these
+            d.w[l] = None
+            d.bias[l] = None
+
+    @property
+    def cout(self):
+        return self.couts[-1]
+
+    def sa_max(self, xyz, new_xyz, feats, idx, out, col_off=0):
+        """Fused SA scale.  xyz [B,N,3], new_xyz [B,S,3], feats [B,N,cfeat] or None,
+        idx [B,S,K] int32, out [B,S,ldo] (written at columns col_off : col_off+cout)."""
+        B, N, _ = xyz.shape
+        S, K = idx.shape[1], idx.shape[2]
+        cfeat = 0 if feats is None else feats.shape[2]
+        f32, i32 = torch.float32, torch.int32
+        _lib.call("sa_mlp_max[N=%d,S=%d,K=%d,C=%d->%s]" % (N, S, K, cfeat + 3, "-".join(map(str, self.couts))),
+                  _lib.load().captra_sa_mlp_max, B, N, S, K, cfeat, _lib.ptr(xyz, f32, "xyz"), _lib.ptr(new_xyz, f32, "new_xyz"),
+            _lib.ptr(feats, f32, "feats") if cfeat else None, _lib.ptr(idx, i32, "idx"),
+            ctypes.byref(self.desc), self.packed.data_ptr(), _lib.ptr(out, f32, "out"),
+            out.shape[-1], col_off, self.impl, _lib.stream_ptr(xyz.device), device=xyz.device)
+        return out
+
+    def rows(self, segA, segB=None, bcast_rows=0, group=0, out=None, col_off=0):
+        """Pointwise MLP.  segA [R,ca] / segB [R,cb] (or [R/bcast_rows,cb]) point-major row blocks
+        (last dim contiguous, arbitrary row stride); returns out [R or R/group, cout]."""
+        f32 = torch.float32
+
+        def seg(t, name):
+            if t is None or t.shape[-1] == 0:
+                return None, 0, 0
+            if not (t.is_cuda and t.dtype == f32 and t.dim() == 2 and t.stride(1) == 1):
+                raise _lib.CaptraError("%s must be a CUDA fp32 [rows, ch] tensor with contiguous channels" % name)
+            return t.data_ptr(), t.stride(0), t.shape[1]
+        pa, lda, ca = seg(segA, "segA")
+        pb, ldb, cb = seg(segB, "segB")
+        R = segA.shape[0] if segA is not None else (segB.shape[0] * max(bcast_rows, 1))
+        nout = R // group if group else R
+        if out is None:
+            out = torch.empty(nout, self.cout, dtype=f32, device=self.device)
+        _lib.call("point_mlp[R=%d,C=%d->%s,g=%d]" % (R, self.cin, "-".join(map(str, self.couts)), group),
+                  _lib.load().captra_point_mlp, R, pa, lda, ca, pb, ldb, cb, bcast_rows, ctypes.byref(self.desc), self.packed.data_ptr(),
+            _lib.ptr(out, f32, "out"), out.shape[-1], col_off, group, self.impl,
+            _lib.stream_ptr(self.device), device=self.device)
+        return out

@@ -1,0 +1,220 @@
+"""Mirror of the tracking-time part of network/models/networks.py + blocks.py: CoordNet,
+RotationRegressionBackbone / RotationRegressor and PartCanonNet with the same constructor
+arguments (cfg dict), the same forward(dict) contract and the same state-dict keys, so the
+reference's checkpoints load and EvalTrackModel.forward (model.py:386-478) can drive them.
+
+Scope note: the backbone and the pose fit are this package's kernels;
+the small per-point heads (seg / NOCS conv1d, RotationRegressor conv1d + GroupNorm) are still
+plain torch modules here, exactly as in the reference -- they are the next row to fuse.  One
+exact saving is already taken: the reference evaluates all P rotation heads on all B*P
+canonicalised clouds and keeps the diagonal (networks.py:200-203); head p is evaluated only on
+part p's copy here, which yields the same tensors.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .backbones import PointNet2Msg
+from .pose_utils.pose_fit import part_fit_st_no_ransac
+
+
+# ---- pose_utils/rotations.py:300-387, part_dof_utils.py:124-141 (elementwise glue) ---------------
+def normalize_vector(v):
+    """rotations.py:300-312."""
+    mag = torch.norm(v, p=2, dim=1, keepdim=True)
+    valid = (mag > 1e-8).float()
+    backup = torch.tensor([1.0, 0.0, 0.0], device=v.device).view(1, 3).expand_as(v)
+    return (v / torch.clamp(mag, min=1e-8)) * valid + backup * (1 - valid)
+
+
+def _proj(u, a):
+    """rotations.py:344-351."""
+    top = (u * a).sum(1)
+    bottom = torch.clamp((u * u).sum(1), min=1e-8)
+    return (top / bottom).unsqueeze(1) * u
+
+
+def compute_rotation_matrix_from_ortho6d(poses):
+    """rotations.py:330-343."""
+    x = normalize_vector(poses[:, 0:3])
+    z = normalize_vector(torch.cross(x, poses[:, 3:6], dim=1))
+    y = torch.cross(z, x, dim=1)
+    return torch.stack((x, y, z), dim=2)
+
+
+def compute_rotation_matrix_from_matrix(m):
+    """rotations.py:354-372: Gram-Schmidt on the columns."""
+    a1, a2, a3 = m[:, :, 0], m[:, :, 1], m[:, :, 2]
+    u2 = a2 - _proj(a1, a2)
+    u3 = a3 - _proj(a1, a3) - _proj(u2, a3)
+    return torch.stack((normalize_vector(a1), normalize_vector(u2), normalize_vector(u3)), dim=2)
+
+
+def compute_rotation_matrix_from_3d(vec):
+    """rotations.py:375-387: y = v/|v|, z = x_raw x y, x = y x z."""
+    y = normalize_vector(vec)
+    x_raw = torch.zeros_like(y)
+    x_raw[..., 0] = 1.0
+    z = normalize_vector(torch.cross(x_raw, y, dim=1))
+    x = torch.cross(y, z, dim=1)
+    return torch.stack((x, y, z), dim=2)
+
+
+def convert_pred_rtvec_to_matrix(pred, sym):
+    """part_dof_utils.py:137-141."""
+    if sym:
+        return compute_rotation_matrix_from_3d(pred.reshape(-1, pred.shape[-1])).reshape(pred.shape[:-1] + (3, 3))
+    return compute_rotation_matrix_from_matrix(pred.reshape(-1, 3, 3)).reshape(pred.shape[:-1] + (3, 3))
+
+
+def canonicalize(cam, points_mean, pose):
+    """networks.py:38-41 / :184-187: (cam + mean - t) -> R^T . -> / s.   cam [B,3,N]."""
+    cam = cam + points_mean - pose['translation']
+    cam = torch.matmul(pose['rotation'].transpose(-1, -2), cam)
+    return cam / pose['scale'].unsqueeze(-1).unsqueeze(-1)
+
+
+# ---- blocks.py:118-193 -----------------------------------------------------------------------
+def get_point_mlp(in_dim, out_dim, dims, acti='none'):
+    """blocks.py:118-135 with dropout=None (networks.py:29-32): conv1d(+bn+relu)* + conv1d + acti."""
+    layers, dims = [], [in_dim] + list(dims) + [out_dim]
+    for i in range(len(dims) - 2):
+        layers += [nn.Conv1d(dims[i], dims[i + 1], 1), nn.BatchNorm1d(dims[i + 1]), nn.ReLU(inplace=True)]
+    layers.append(nn.Conv1d(dims[-2], dims[-1], 1))
+    if acti == 'sigmoid':
+        layers.append(nn.Sigmoid())
+    return nn.Sequential(*layers)
+
+
+class MLPConv1d(nn.Module):
+    """blocks.py:146-165 with gn=True: conv1d + GroupNorm(C/2 groups) + ReLU per hidden layer."""
+
+    def __init__(self, in_channel, mlp):
+        super().__init__()
+        layers, last = [], in_channel
+        for i, out_channel in enumerate(mlp):
+            layers.append(nn.Conv1d(last, out_channel, 1))
+            if i != len(mlp) - 1:
+                layers += [nn.GroupNorm(out_channel // 2, out_channel), nn.ReLU(inplace=True)]
+            last = out_channel
+        self.model = nn.Sequential(*layers)
+        self.out_channel = last
+
+    def forward(self, x):
+        return self.model(x)
+
+
+class RotationRegressor(nn.Module):
+    """blocks.py:168-193."""
+
+    def __init__(self, in_dim, num_parts, symmetric=False):
+        super().__init__()
+        self.sym = symmetric
+        rot_dim = 3 if symmetric else 6
+        self.rtvec_head = nn.ModuleList([MLPConv1d(in_dim, [512, 512, 256, rot_dim]) for _ in range(num_parts)])
+        self.num_parts = num_parts
+
+    def post(self, rtvec):
+        """[..., D, N] raw head output -> per-point unit vector (sym) or 3x3 (9 rows)."""
+        raw = rtvec.transpose(-1, -2)
+        shape = raw.shape
+        if self.sym:
+            return normalize_vector(raw.reshape(-1, 3)).reshape(shape).transpose(-1, -2)
+        rot = compute_rotation_matrix_from_ortho6d(raw.reshape(-1, 6))
+        return rot.reshape(shape[:-1] + (-1,)).transpose(-1, -2)
+
+    def forward(self, feat):  # [B, in_dim, N] -> [B, P, R, N]
+        return self.post(torch.stack([head(feat) for head in self.rtvec_head], dim=1))
+
+
+class CoordNet(nn.Module):
+    """networks.py:19-110 (tracking-time forward: no 'gt_part' in the input, model.py:349-362)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.backbone = PointNet2Msg(cfg, cfg['network']['backbone_out_dim'], net_type='camera', use_xyz_feat=True)
+        in_dim = cfg['network']['backbone_out_dim']
+        self.num_parts = cfg['num_parts']
+        self.sym = cfg['obj_sym']
+        seg_dim = self.num_parts + cfg['obj']['extra_dims']
+        self.seg_head = get_point_mlp(in_dim, seg_dim, [], acti='none')
+        self.nocs_head = get_point_mlp(in_dim, 3 * self.num_parts, cfg['network']['nocs_head_dims'], acti='sigmoid')
+
+    def forward(self, input, test=False):
+        cam = canonicalize(input['points'], input['points_mean'], input['canon_pose'])
+        feat = self.backbone(cam)
+        seg = F.softmax(self.seg_head(feat), dim=1)
+        nocs = self.nocs_head(feat) - 0.5
+        assert 'gt_part' not in input, "training-time pose branch (networks.py:54-108) is not mirrored"
+        return {'seg': seg, 'nocs': nocs, 'points': cam}
+
+
+class RotationRegressionBackbone(nn.Module):
+    """networks.py:113-141."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.num_parts = cfg['num_parts']
+        self.encoder = PointNet2Msg(cfg, cfg['network']['backbone_out_dim'], use_xyz_feat=False)
+        self.sym = cfg['obj_sym']
+        self.pose_pred = RotationRegressor(cfg['network']['backbone_out_dim'], self.num_parts, symmetric=self.sym)
+
+    def forward_diag(self, cam, labels, batch_size):
+        """cam [B*P,3,N] (copy p canonicalised by part p), labels [B,N] -> rtvec [B,P,D]: head p on
+        copy p, masked mean over part p's points (networks.py:127-139 restricted to the diagonal
+        that networks.py:200-203 keeps)."""
+        P = self.num_parts
+        feat = self.encoder(cam)                                   # [B*P, C, N]
+        feat = feat.reshape(batch_size, P, feat.shape[1], feat.shape[2])
+        out = []
+        for p in range(P):
+            raw = self.pose_pred.post(self.pose_pred.rtvec_head[p](feat[:, p]))   # [B, D, N]
+            mask = (labels == p).float().unsqueeze(1)                               # [B, 1, N]
+            cnt = mask.sum(-1)
+            mean = (raw * mask).sum(-1) / torch.clamp_min(cnt, 1.0)
+            default = torch.tensor((0., 1., 0.)) if self.sym else torch.eye(3).reshape(-1)
+            valid = (cnt > 0).float()
+            out.append(valid * mean + (1.0 - valid) * default.to(raw.device).reshape(1, -1))
+        return torch.stack(out, dim=1)
+
+
+class PartCanonNet(nn.Module):
+    """networks.py:144-239, network type 'rot_coord_track', test_mode=True (the tracker's call)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.type = cfg['network']['type']
+        assert self.type == 'rot_coord_track', "only the tracking network type is mirrored"
+        self.regress_net = RotationRegressionBackbone(cfg)
+        self.device = cfg['device']
+        self.num_parts = cfg['num_parts']
+        self.sym = cfg['obj_sym']
+        self.tree = cfg['obj_tree']
+        self.root = [i for i in range(self.num_parts) if self.tree[i] == -1][0]
+        self.cfg = cfg
+
+    def forward(self, input, test_mode=True):
+        assert test_mode, "training-time branches are not mirrored"
+        part_pose = input['state']['part']
+        P = self.num_parts
+        canon_pose = input.get('canon_pose') or {
+            key: part_pose[key].reshape((-1,) + part_pose[key].shape[2:]) for key in ('rotation', 'translation', 'scale')}
+        cam = input['points']                       # [B,3,N]
+        B = len(cam)
+        points_mean = input['points_mean']          # [B,3,1]
+        labels = input['pred_labels']               # [B,N]
+        cam_rep = cam.unsqueeze(1).expand(-1, P, -1, -1).reshape((-1,) + cam.shape[-2:])
+        mean_rep = points_mean.unsqueeze(1).expand(-1, P, -1, -1).reshape((-1,) + points_mean.shape[-2:])
+        cam_rep = canonicalize(cam_rep, mean_rep, canon_pose)
+        rtvec = self.regress_net.forward_diag(cam_rep, labels, B)              # [B,P,D]
+        delta_rot = convert_pred_rtvec_to_matrix(rtvec, self.sym)                # [B,P,3,3]
+        rotation = torch.matmul(part_pose['rotation'], delta_rot)                # part_dof_utils.py:124-128
+        pred_npcs = input['pred_nocs'].reshape(B, P, 3, -1)
+        cam_points = (cam + points_mean).unsqueeze(1).expand(-1, P, -1, -1)
+        final_pose, valid = part_fit_st_no_ransac(labels, pred_npcs.transpose(-1, -2), cam_points.transpose(-1, -2),
+                                                  rotation, {'num_parts': P, 'sym': self.sym})
+        v = valid.float()
+        final_pose['scale'] = v * final_pose['scale'] + (1.0 - v) * part_pose['scale']
+        v = v.unsqueeze(-1).unsqueeze(-1)
+        final_pose['translation'] = v * final_pose['translation'] + (1.0 - v) * part_pose['translation']
+        return {'part': final_pose}

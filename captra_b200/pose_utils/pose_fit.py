@@ -56,12 +56,12 @@ def part_fit_st_no_ransac(labels, source, target, rotation, cfg, given_scale=Non
     valid = torch.empty(B, P, dtype=torch.uint8, device=dev)
     rot_used = torch.empty(B, P, 3, 3, dtype=torch.float32, device=dev) if rotation is None else None
     ss, ts = source.stride(), target.stride()
-    _lib.check(_lib.load().captra_part_fit_st(
+    _lib.call("part_fit_st[P=%d,N=%d]" % (P, N), _lib.load().captra_part_fit_st,
         B, P, N, labels.data_ptr(), None,
         source.data_ptr(), ss[0], ss[1], ss[2], ss[3],
         target.data_ptr(), ts[0], ts[1], ts[2], ts[3],
         rot.data_ptr() if rot is not None else None, gs.data_ptr() if gs is not None else None,
         1 if cfg["sym"] else 0, scale.data_ptr(), translation.data_ptr(), valid.data_ptr(),
-        rot_used.data_ptr() if rot_used is not None else None, _lib.stream_ptr(dev)), "part_fit_st")
+        rot_used.data_ptr() if rot_used is not None else None, _lib.stream_ptr(dev), device=dev)
     model = {"rotation": rotation if rotation is not None else rot_used, "scale": scale, "translation": translation}
     return model, valid.bool()

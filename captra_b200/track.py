@@ -1,0 +1,112 @@
+"""Per-frame tracking step (the loop body of EvalTrackModel.forward, model.py:409-478) on top of
+the B200 kernels, plus the synthetic workloads of BASELINE.json used by bench.py and the tests.
+
+One "frame" = CoordNet forward on B clouds + argmax labels + PartCanonNet forward on B*P
+canonicalised clouds + fused pose fit -> the new 9-DoF part poses for B trajectories.
+"""
+import numpy as np
+import torch
+
+from . import synthetic
+from .networks import CoordNet, PartCanonNet
+
+
+def default_pointnet_cfg():
+    """configs/pointnet_config/pointnet2_camera.yml:1-44 (the unused lstm*/flow1 keys dropped)."""
+    return {
+        "sa1": {"npoint": 512, "radius_list": [0.05, 0.1, 0.2], "nsample_list": [32, 64, 128],
+                "mlp_list": [[32, 32, 64], [64, 64, 128], [64, 96, 128]]},
+        "sa2": {"npoint": 128, "radius_list": [0.2, 0.4], "nsample_list": [64, 128],
+                "mlp_list": [[128, 128, 256], [128, 196, 256]]},
+        "sa3": {"mlp": [256, 512, 1024]},
+        "fp3": {"mlp": [256, 256]}, "fp2": {"mlp": [256, 128]}, "fp1": {"mlp": [128, 128]},
+    }
+
+
+CATEGORIES = {
+    # configs/obj_config/obj_info_nocs.yml:6-20 (bottle; bowl/can identical) and
+    # obj_info_sapien.yml:52-65 (laptop); network section of config_track.yml:33-37
+    "bottle": dict(num_parts=1, sym=True, tree=[-1], extra_dims=1),
+    "laptop": dict(num_parts=2, sym=False, tree=[-1, 0], extra_dims=0),
+}
+
+
+def make_cfg(category="bottle", device="cuda:0"):
+    c = CATEGORIES[category]
+    return {
+        "pointnet": {"camera": default_pointnet_cfg()}, "device": device,
+        "network": {"type": "rot_coord_track", "backbone_out_dim": 128, "nocs_head_dims": [128]},
+        "num_parts": c["num_parts"], "obj_sym": c["sym"], "obj_tree": c["tree"],
+        "obj": {"extra_dims": c["extra_dims"]}, "num_points": 4096,
+    }
+
+
+def init_weights(module, seed=0):
+    """Reference init (trainer.py:111: xavier, gain sqrt(2)) + randomised BN running stats so the
+    folded-BN path is exercised.  Deterministic for a given torch build."""
+    gen = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d)):
+            fan_in = m.in_channels
+            fan_out = m.out_channels
+            std = (2.0 ** 0.5) * (2.0 / (fan_in + fan_out)) ** 0.5
+            m.weight.data.copy_(torch.randn(m.weight.shape, generator=gen) * std)
+            m.bias.data.zero_()
+        elif isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) + 0.5)
+    return module
+
+
+class Tracker(torch.nn.Module):
+    """npcs_net + net of EvalTrackModel (model.py:312-313)."""
+
+    def __init__(self, cfg, seed=0):
+        super().__init__()
+        self.cfg = cfg
+        self.npcs_net = init_weights(CoordNet(cfg), seed)
+        self.net = init_weights(PartCanonNet(cfg), seed + 1)
+        self.num_parts = cfg["num_parts"]
+        self.root = [p for p in range(self.num_parts) if cfg["obj_tree"][p] == -1][0]
+
+    @torch.no_grad()
+    def step(self, points, points_mean, last_pose):
+        """model.py:454-476.  points [B,3,N] (mean-subtracted), points_mean [B,3,1],
+        last_pose {'rotation' [B,P,3,3], 'translation' [B,P,3,1], 'scale' [B,P]} -> new pose dict."""
+        canon = {k: last_pose[k][:, self.root] for k in ("rotation", "translation", "scale")}
+        pred = self.npcs_net({"points": points, "points_mean": points_mean, "canon_pose": canon})
+        B = points.shape[0]
+        pred_npcs = pred["nocs"].reshape(B, self.num_parts, 3, -1)
+        pred_labels = torch.max(pred["seg"], dim=-2)[1]
+        out = self.net({"points": points, "points_mean": points_mean, "state": {"part": last_pose},
+                        "pred_labels": pred_labels, "pred_nocs": pred_npcs}, test_mode=True)
+        return out["part"]
+
+
+def synthetic_track_batch(b, category="bottle", n=4096, seed=0):
+    """Host-side (numpy, float32) inputs of one frame for b trajectories: mean-subtracted camera
+    points [b,3,n], their mean [b,3,1] and a perturbed initial pose per part (pose_perturb of
+    config_track.yml:46-50: r=5 deg, t=0.03, s=0.02)."""
+    c = CATEGORIES[category]
+    P = c["num_parts"]
+    case = synthetic.pose_fit_case(b, P, n, seed=seed, sym=False)
+    rng = np.random.default_rng(seed + 1)
+    cam = case["cam"]                                  # [b,n,3]
+    mean = cam.mean(1, keepdims=True)
+    points = np.ascontiguousarray(np.swapaxes(cam - mean, 1, 2)).astype(np.float32)
+    R = case["R"].copy()
+    for bi in range(b):
+        for pi in range(P):
+            axis = rng.normal(size=3)
+            axis /= np.linalg.norm(axis)
+            ang = np.deg2rad(5.0) * rng.normal()
+            K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+            dR = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+            R[bi, pi] = R[bi, pi] @ dR
+    pose = {
+        "rotation": R.astype(np.float32),
+        "translation": (case["t"] + rng.normal(scale=0.03, size=case["t"].shape))[..., None].astype(np.float32),
+        "scale": (case["s"] + rng.normal(scale=0.02, size=case["s"].shape)).astype(np.float32),
+    }
+    return {"points": points, "points_mean": np.swapaxes(mean, 1, 2).astype(np.float32), "pose": pose,
+            "gt": {"rotation": case["R"], "translation": case["t"][..., None], "scale": case["s"]}}

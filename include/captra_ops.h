@@ -135,21 +135,34 @@ typedef struct {
     int relu_last;                        /* apply ReLU after the last layer */
 } captra_mlp_desc;
 
+/* Weights are re-laid-out once per model load into a caller-owned device buffer ("packed",
+ * 16-byte aligned, captra_mlp_pack_bytes() bytes); the execution calls take the same desc (only
+ * nlayers/cin/cout/relu_last are read there) plus that buffer.  impl: 0 = exact-fp32 CUDA-core
+ * kernel, 1 = tcgen05 3xTF32 kernel (packs are impl-specific). */
+int64_t captra_mlp_pack_bytes(const captra_mlp_desc *mlp, int impl);
+int captra_mlp_pack(const captra_mlp_desc *mlp, int impl, void *packed, captra_stream_t stream);
+
 /* Fused set-abstraction scale (pointnet_utils.py:233-246): for every centroid s and sample k
- *   row = [ feats[b, :, idx[b,s,k]] (cfeat ch) , xyz[b, idx[b,s,k], :] - new_xyz[b,s,:] (3 ch) ]
- * -> MLP (ReLU after every layer) -> max over k -> out[b, out_ch_offset + c, s].
- * feats is POINT-major [B,N,cfeat] (may be NULL when cfeat==0); out is [B, out_ch_total, S].
- * impl: 0 = fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel. */
+ *   row = [ feats[b, idx[b,s,k], :] (cfeat ch) , xyz[b, idx[b,s,k], :] - new_xyz[b,s,:] (3 ch) ]
+ * -> MLP (ReLU after every layer) -> max over k -> out[(b*S+s)*ldo + col_off + c].
+ * feats is POINT-major [B,N,cfeat] (NULL when cfeat==0), xyz [B,N,3], new_xyz [B,S,3],
+ * idx [B,S,K] int32; out is point-major with row stride ldo, so the scales of one MSG layer
+ * write side by side into one [B,S,sum(cout)] tensor (the torch.cat of pointnet_utils.py:249). */
 int captra_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz,
                       const float *new_xyz, const float *feats, const int *idx,
-                      const captra_mlp_desc *mlp, float *out, int out_ch_total,
-                      int out_ch_offset, int impl, captra_stream_t stream);
+                      const captra_mlp_desc *mlp, const void *packed, float *out, int64_t ldo,
+                      int col_off, int impl, captra_stream_t stream);
 
-/* Pointwise MLP on rows: x [rows, cin] row-major (point-major) -> y [rows, cout_last].
- * If group > 0 a max over each consecutive `group` rows is taken (group-all SA,
- * pointnet_utils.py:337-343) and y is [rows/group, cout_last]. */
-int captra_point_mlp(int64_t rows, const float *x, const captra_mlp_desc *mlp, float *y,
-                     int group, int impl, captra_stream_t stream);
+/* Pointwise MLP on rows.  Row r of the input is the concatenation
+ *   [ segA[r*ldA : +ca] , segB[(bcast_rows ? r / bcast_rows : r)*ldB : +cb] ]
+ * (the torch.cat of pointnet_utils.py:185,292 and the `repeat` of :281-282 without
+ * materialising them).  If group > 0 a max over each `group` consecutive rows follows the last
+ * layer (group-all SA, pointnet_utils.py:337-343).  Output row r (or group g) is written at
+ * y + r*ldy + col_off. */
+int captra_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB,
+                     int64_t ldB, int cb, int bcast_rows, const captra_mlp_desc *mlp,
+                     const void *packed, float *y, int64_t ldy, int col_off, int group, int impl,
+                     captra_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 4. Pose fit (pose_utils/procrustes.py, pose_utils/pose_fit.py) -- Python in the reference,
