@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- tracking frames/s @ 4096 points on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one tracking frame for a batch of trajectories (the loop body of
+EvalTrackModel.forward, model.py:409-478): CoordNet forward on B clouds, argmax labels,
+RotationNet forward on B*P canonicalised clouds, fused pose fit.  Workload (config.workload):
+BASELINE.json configs[1] "NOCS bottle, batch 32 x 4096 pts" per GPU; with N GPUs every rank tracks
+its own 32 trajectories (weak scaling, no data-path collective) and the end-of-step pose-error
+scalars are summed with one NCCL all-reduce.
+
+value : frames/s with the step's inputs already resident in HBM; per-step CUDA-event pairs on the
+        launching stream, L2 flushed between steps (outside the pairs), max over ranks.
+e2e   : same metric through the public API from HOST buffers: each step copies that step's points /
+        means / poses from pinned host memory, runs Tracker.step, and reads the new poses back.
+roofline / kernels : a separate profiled pass brackets every C-ABI launch with CUDA events.
+cpu_baseline : oracle/frame_ref (CPU restatement in the reference's structure, "port") timed on this
+        host's cores on a bounded sample.  --impl reference prints the same measurement as its own line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    "cfg2": dict(category="bottle", batch=32, desc="NOCS-REAL275 rigid (bottle, sym), batch 32 x 4096 pts, full track step"),
+    "cfg3": dict(category="laptop", batch=16, desc="SAPIEN articulated (laptop, 2 parts), batch 16 x 4096 pts, full track step"),
+}
+METRIC = "tracking frames/sec @4096 pts"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# algorithmic work per launch, keyed on the launch tags of captra_b200._lib.call
+# --------------------------------------------------------------------------------------------
+def _parse(tag):
+    name, _, rest = tag.partition("[")
+    kv = {}
+    for item in rest.rstrip("]").split(","):
+        if "=" in item:
+            k, v = item.split("=", 1)
+            kv[k] = v
+    return name, kv
+
+
+def algorithmic(tag):
+    """(bytes, flops) per launch; the batch size is part of the tag."""
+    name, kv = _parse(tag)
+    B = int(kv.get("B", 1))
+    if name == "ball_query_multi":
+        N, S = int(kv["N"]), int(kv["S"])
+        Ks = [int(k) for k in kv["K"].split("/")]
+        return 12 * B * (N + S) + 4 * B * S * sum(Ks), 8 * B * S * N
+    if name == "fps_gather":
+        N, M = int(kv["N"]), int(kv["M"])
+        return 12 * B * N + 4 * B * M + 12 * B * M, 8 * B * N * (M - 1)
+    if name == "three_nn_interpolate":
+        n, m, C = int(kv["n"]), int(kv["m"]), int(kv["C"])
+        return 12 * B * (n + m) + 4 * B * C * m + 4 * B * C * n, 8 * B * n * m + 6 * B * C * n
+    if name == "sa_mlp_max":
+        N, S, K = int(kv["N"]), int(kv["S"]), int(kv["K"])
+        cin, widths = kv["C"].split("->")
+        cin, widths = int(cin), [int(w) for w in widths.split("-")]
+        rows = B * S * K
+        macs, last = 0, cin
+        for w in widths:
+            macs += last * w
+            last = w
+        wbytes = 4 * sum(a * b for a, b in zip([cin] + widths[:-1], widths))
+        # compulsory traffic of the fused query-group-MLP-max: xyz + features once, idx, output, weights
+        return 12 * B * (N + S) + 4 * B * (cin - 3) * N + 4 * B * S * K + 4 * B * S * widths[-1] + wbytes, 2 * rows * macs
+    if name == "point_mlp":
+        R, g = int(kv["R"]), int(kv["g"])
+        cin, widths = kv["C"].split("->")
+        cin, widths = int(cin), [int(w) for w in widths.split("-")]
+        macs, last = 0, cin
+        for w in widths:
+            macs += last * w
+            last = w
+        out_rows = R // g if g else R
+        wbytes = 4 * sum(a * b for a, b in zip([cin] + widths[:-1], widths))
+        return 4 * R * cin + 4 * out_rows * widths[-1] + wbytes, 2 * R * macs
+    if name == "part_fit_st":
+        P, N = int(kv["P"]), int(kv["N"])
+        nb = B
+        return 2 * 12 * nb * P * N + 8 * nb * N + 52 * nb * P, 60 * nb * P * N
+    return 0, 0
+
+
+def setup_dist(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def host_batches(workload, rank, nbatch):
+    from captra_b200 import track
+    w = WORKLOADS[workload]
+    out = []
+    for i in range(nbatch):
+        b = track.synthetic_track_batch(w["batch"], w["category"], n=4096, seed=1000 * rank + i)
+        out.append(b)
+    return out
+
+
+def pin(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+
+def cpu_reference_arm(workload, steps, warmup, sample_clouds):
+    """Times oracle/frame_ref.track_step (CPU port in the reference's structure) with all host threads."""
+    from captra_b200 import track
+    from oracle import cpu_ref, frame_ref
+    w = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_ref.set_num_threads(cores)
+    cfg = track.make_cfg(w["category"], device="cpu")
+    trk = track.Tracker(cfg, seed=0).eval()
+    sd_c = {k: v.detach() for k, v in trk.npcs_net.state_dict().items()}
+    sd_r = {k: v.detach() for k, v in trk.net.state_dict().items()}
+    b = track.synthetic_track_batch(sample_clouds, w["category"], n=4096, seed=0)
+    pts, mean = torch.from_numpy(b["points"]), torch.from_numpy(b["points_mean"])
+    pose = {k: torch.from_numpy(v) for k, v in b["pose"].items()}
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            frame_ref.track_step(sd_c, sd_r, cfg, pts, mean, pose)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = float(np.sum(times))
+    return {"value": sample_clouds * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d of %d clouds per step x %d steps (%d warm-up), oracle/frame_ref.track_step, torch %d threads + OpenMP %d" % (
+                sample_clouds, w["batch"], len(times), warmup, cores, cpu_ref.num_threads()),
+            "ms_per_step": 1e3 * total / len(times), "median_ms": 1e3 * float(np.median(times)), "best_ms": 1e3 * float(np.min(times))}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=4, help="clouds per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    config = {"workload": w["desc"], "name": args.workload, "points": 4096, "batch_per_gpu": w["batch"],
+              "category": w["category"], "weights": "random init (seeded), BN stats randomised, eval mode"}
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return 0
+        steps = min(args.steps, 5)
+        r = cpu_reference_arm(args.workload, steps, min(args.warmup, 1), args.cpu_sample)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    world, rank, local = setup_dist(args)
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU path)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = False   # heads are torch fp32; keep them true fp32 like the reference
+    torch.backends.cudnn.allow_tf32 = False
+    from captra_b200 import _lib, track
+    _lib.load()
+    cfg = track.make_cfg(w["category"], device=str(dev))
+    trk = track.Tracker(cfg, seed=0).to(dev).eval()
+    B, P = w["batch"], cfg["num_parts"]
+
+    nb = 4  # distinct host batches, cycled
+    hb = host_batches(args.workload, rank, nb)
+    pinned = [dict(points=pin(b["points"]), mean=pin(b["points_mean"]), pose={k: pin(v) for k, v in b["pose"].items()},
+                   gt={k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(dev) for k, v in b["gt"].items()}) for b in hb]
+    resident = [dict(points=p["points"].to(dev), mean=p["mean"].to(dev), pose={k: v.to(dev) for k, v in p["pose"].items()}) for p in pinned]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def loss_scalars(pose, gt):
+        """pose-error scalars a tracker logs per batch (model.py:511-593 in spirit): sums + count."""
+        t_err = (pose["translation"] - gt["translation"]).norm(dim=-2).sum()
+        s_err = (pose["scale"] - gt["scale"]).abs().sum()
+        r_err = (pose["rotation"] - gt["rotation"]).pow(2).sum()
+        return torch.stack([t_err, s_err, r_err, torch.tensor(float(B * P), device=dev)])
+
+    def step_resident(i):
+        r = resident[i % nb]
+        pose = trk.step(r["points"], r["mean"], r["pose"])
+        ls = loss_scalars(pose, pinned[i % nb]["gt"])
+        if world > 1:
+            torch.distributed.all_reduce(ls)
+        return pose, ls
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                      # L2 flush, outside the event pair
+        ev[i][0].record(stream)
+        step_resident(i)
+        ev[i][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _lib.launch_count() - l0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(np.sum(step_ms))
+
+    # ---- end-to-end from host buffers --------------------------------------------------------
+    h2d = int(pinned[0]["points"].numel() * 4 + pinned[0]["mean"].numel() * 4 + sum(v.numel() * 4 for v in pinned[0]["pose"].values()))
+    out_host = {k: torch.empty_like(v).pin_memory() for k, v in pinned[0]["pose"].items()}
+    d2h = int(sum(v.numel() * 4 for v in out_host.values()))
+
+    def step_e2e(i):
+        p = pinned[i % nb]
+        pts = p["points"].to(dev, non_blocking=True)
+        mean = p["mean"].to(dev, non_blocking=True)
+        pose = {k: v.to(dev, non_blocking=True) for k, v in p["pose"].items()}
+        new = trk.step(pts, mean, pose)
+        if world > 1:
+            torch.distributed.all_reduce(loss_scalars(new, p["gt"]))
+        for k in out_host:
+            out_host[k].copy_(new[k], non_blocking=True)
+        stream.synchronize()               # the tracker consumes the pose of frame t before frame t+1
+
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        ev2[i][0].record(stream)
+        step_e2e(i)
+        ev2[i][1].record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = float(np.sum([a.elapsed_time(b) for a, b in ev2]))
+
+    # ---- max over ranks -----------------------------------------------------------------------
+    tt = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    total_ms, e2e_ms = float(tt[0]), float(tt[1])
+    frames = B * args.steps * world
+
+    # ---- profiled pass: per-launch CUDA events (rank 0) -----------------------------------------
+    kernels, roofline = [], None
+    if rank == 0:
+        pk = peaks()
+        _lib.PROFILE = []
+        nprof = 3
+        for i in range(nprof):
+            flush.zero_()
+            step_resident(i)
+        torch.cuda.synchronize(dev)
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        agg = {}
+        for tag, e0, e1 in prof:
+            agg.setdefault(tag, []).append(e0.elapsed_time(e1))
+        step_avg_ms = total_ms / args.steps
+        for tag, ts in agg.items():
+            per_step = len(ts) / nprof
+            avg = float(np.mean(ts))
+            kernels.append(dict(tag=tag, launches_per_step=per_step, avg_us=1e3 * avg, ms_per_step=avg * per_step))
+        for k in kernels:
+            by, fl = algorithmic(k["tag"])
+            k["alg_bytes"], k["alg_flops"] = by, fl
+            k["gbs"] = by / (k["avg_us"] * 1e-6) / 1e9 if k["avg_us"] > 0 else 0.0
+            k["tflops"] = fl / (k["avg_us"] * 1e-6) / 1e12 if k["avg_us"] > 0 else 0.0
+            k["hbm_frac"] = k["gbs"] / pk["hbm"]
+            k["share_of_step"] = k["ms_per_step"] / step_avg_ms
+        kernels.sort(key=lambda k: -k["ms_per_step"])
+        top = kernels[0]
+        tname = _parse(top["tag"])[0]
+        if tname in ("sa_mlp_max", "point_mlp"):
+            roofline = {"kernel": top["tag"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tf_sus"], "unit": "TFLOP/s",
+                        "frac": top["tflops"] / pk["tf_sus"], "traffic": None,
+                        "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); algorithmic flops = 2*rows*sum(Cin*Cout), each MAC counted once" % pk["src"],
+                        "avg_us": top["avg_us"], "share_of_step": top["share_of_step"]}
+        else:
+            roofline = {"kernel": top["tag"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": top["hbm_frac"], "traffic": None, "peak_source": pk["src"] + " hbm_gbs",
+                        "avg_us": top["avg_us"], "share_of_step": top["share_of_step"]}
+        bq = [k for k in kernels if _parse(k["tag"])[0] in ("ball_query_multi", "sa_mlp_max")]
+        qg_bytes = sum(k["alg_bytes"] * k["launches_per_step"] for k in bq)
+        qg_ms = sum(k["ms_per_step"] for k in bq)
+        query_group = {"what": "ball_query + fused group/MLP/max launches of one step", "alg_bytes_per_step": qg_bytes,
+                       "ms_per_step": qg_ms, "gbs": qg_bytes / (qg_ms * 1e-3) / 1e9 if qg_ms else 0.0,
+                       "frac_of_hbm_peak": (qg_bytes / (qg_ms * 1e-3) / 1e9) / pk["hbm"] if qg_ms else 0.0}
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return 0
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_arm(args.workload, 2, 1, args.cpu_sample)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": METRIC, "value": frames / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
+                                            mlp_impl=int(os.environ.get("CAPTRA_MLP_IMPL", "0")),
+                                            heads="torch fp32 (next row, SURVEY 8f-1)", collective="nccl all_reduce of 4 pose-error scalars per step" if world > 1 else "none"),
+        "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clocks,
+        "roofline": roofline, "query_group": query_group, "kernels": kernels[:12], "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -35,6 +35,7 @@ SIGNATURES = {
     "captra_mlp_pack": [_P, c_int, _P, _P],
     "captra_sa_mlp_max": [c_int] * 5 + [_P] * 7 + [c_i64, c_int, c_int, _P],
     "captra_point_mlp": [c_i64, _P, c_i64, c_int, _P, c_i64, c_int, c_int, _P, _P, _P, c_i64, c_int, c_int, c_int, _P],
+    "captra_debug_umma_gemm": [c_int, c_int, _P, _P, _P, c_int, _P],
     "captra_procrustes_rot3": [c_i64, _P, _P, _P],
     "captra_procrustes_rot2": [c_i64, _P, _P, _P],
     "captra_part_fit_st": [c_int] * 3 + [_P, _P] + [_P] + [c_i64] * 4 + [_P] + [c_i64] * 4 + [_P, _P, c_int, _P, _P, _P, _P, _P],

@@ -15,7 +15,7 @@ def fps_gather(xyz, npoint):
     idx = torch.empty(B, npoint, dtype=_i32, device=xyz.device)
     new_xyz = torch.empty(B, npoint, 3, dtype=_f32, device=xyz.device)
     temp = torch.full((B, N), 1e10, dtype=_f32, device=xyz.device)
-    _lib.call("fps_gather[N=%d,M=%d]" % (N, npoint), _lib.load().captra_fps_gather, B, N, npoint,
+    _lib.call("fps_gather[B=%d,N=%d,M=%d]" % (B, N, npoint), _lib.load().captra_fps_gather, B, N, npoint,
               _lib.ptr(xyz, _f32, "xyz"), temp.data_ptr(), idx.data_ptr(), new_xyz.data_ptr(),
               _lib.stream_ptr(xyz.device), device=xyz.device)
     return idx, new_xyz
@@ -30,7 +30,7 @@ def ball_query_multi(radii, nsamples, xyz, new_xyz):
     ra = (ctypes.c_float * nr)(*[float(r) for r in radii])
     ka = (ctypes.c_int * nr)(*[int(k) for k in nsamples])
     pa = (ctypes.c_void_p * nr)(*[o.data_ptr() for o in outs])
-    _lib.call("ball_query_multi[N=%d,S=%d,K=%s]" % (N, S, "/".join(map(str, nsamples))),
+    _lib.call("ball_query_multi[B=%d,N=%d,S=%d,K=%s]" % (B, N, S, "/".join(map(str, nsamples))),
               _lib.load().captra_ball_query_multi, B, N, S, nr, ra, ka, _lib.ptr(new_xyz, _f32, "new_xyz"),
               _lib.ptr(xyz, _f32, "xyz"), pa, _lib.stream_ptr(xyz.device), device=xyz.device)
     return outs
@@ -46,7 +46,7 @@ def three_nn_interpolate_pm(unknown, known, feats_pm, out=None, col_off=0):
     w = torch.empty(B, n, 3, dtype=_f32, device=dev)
     if out is None:
         out = torch.empty(B, n, C, dtype=_f32, device=dev)
-    _lib.call("three_nn_interpolate[n=%d,m=%d,C=%d]" % (n, m, C), _lib.load().captra_three_nn_interpolate,
+    _lib.call("three_nn_interpolate[B=%d,n=%d,m=%d,C=%d]" % (B, n, m, C), _lib.load().captra_three_nn_interpolate,
               B, C, n, m, _lib.ptr(unknown, _f32, "unknown"), _lib.ptr(known, _f32, "known"),
         _lib.ptr(feats_pm, _f32, "feats"), _lib.ptr(out, _f32, "out"), None, idx.data_ptr(), w.data_ptr(),
         1, out.shape[-1], col_off, _lib.stream_ptr(dev), device=dev)

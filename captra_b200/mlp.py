@@ -84,7 +84,7 @@ class PackedMLP:
         S, K = idx.shape[1], idx.shape[2]
         cfeat = 0 if feats is None else feats.shape[2]
         f32, i32 = torch.float32, torch.int32
-        _lib.call("sa_mlp_max[N=%d,S=%d,K=%d,C=%d->%s]" % (N, S, K, cfeat + 3, "-".join(map(str, self.couts))),
+        _lib.call("sa_mlp_max[B=%d,N=%d,S=%d,K=%d,C=%d->%s]" % (B, N, S, K, cfeat + 3, "-".join(map(str, self.couts))),
                   _lib.load().captra_sa_mlp_max, B, N, S, K, cfeat, _lib.ptr(xyz, f32, "xyz"), _lib.ptr(new_xyz, f32, "new_xyz"),
             _lib.ptr(feats, f32, "feats") if cfeat else None, _lib.ptr(idx, i32, "idx"),
             ctypes.byref(self.desc), self.packed.data_ptr(), _lib.ptr(out, f32, "out"),

@@ -56,7 +56,7 @@ def part_fit_st_no_ransac(labels, source, target, rotation, cfg, given_scale=Non
     valid = torch.empty(B, P, dtype=torch.uint8, device=dev)
     rot_used = torch.empty(B, P, 3, 3, dtype=torch.float32, device=dev) if rotation is None else None
     ss, ts = source.stride(), target.stride()
-    _lib.call("part_fit_st[P=%d,N=%d]" % (P, N), _lib.load().captra_part_fit_st,
+    _lib.call("part_fit_st[B=%d,P=%d,N=%d]" % (B, P, N), _lib.load().captra_part_fit_st,
         B, P, N, labels.data_ptr(), None,
         source.data_ptr(), ss[0], ss[1], ss[2], ss[3],
         target.data_ptr(), ts[0], ts[1], ts[2], ts[3],

@@ -194,6 +194,13 @@ int captra_part_fit_st(int b, int p, int n, const int64_t *labels, const float *
                        float *translation, uint8_t *valid, float *rot_out,
                        captra_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * 5. Unit-test doorway for the tcgen05 primitives: D[128,n] = A[128,k] * W[n,k]^T on one CTA
+ *    (terms = 1: single-pass TF32, 3: 3xTF32).  Not used by the product path.
+ * ---------------------------------------------------------------------------------------- */
+int captra_debug_umma_gemm(int k, int n, const float *A, const float *W, float *D, int terms,
+                           captra_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
