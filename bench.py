@@ -386,7 +386,7 @@ def main():
         "metric": METRIC, "value": frames / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
-                                            mlp_impl=int(os.environ.get("CAPTRA_MLP_IMPL", "0")),
+                                            mlp_impl=int(os.environ.get("CAPTRA_MLP_IMPL", "1")),
                                             heads="torch fp32 (next row, SURVEY 8f-1)", collective="nccl all_reduce of 4 pose-error scalars per step" if world > 1 else "none"),
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},

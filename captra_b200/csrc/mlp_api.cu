@@ -10,6 +10,14 @@ int simt_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, con
 int simt_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB,
                    int cb, int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
                    int col_off, int group, cudaStream_t stream);
+int64_t tc_pack_bytes(const captra_mlp_desc *d);
+int tc_pack(const captra_mlp_desc *d, void *packed, cudaStream_t stream);
+int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const float *new_xyz,
+                  const float *feats, const int *idx, const captra_mlp_desc *d, const void *packed,
+                  float *out, int64_t ldo, int col_off, cudaStream_t stream);
+int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
+                 int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
+                 cudaStream_t stream);
 }  // namespace captra
 
 using namespace captra;
@@ -17,6 +25,11 @@ using namespace captra;
 extern "C" int64_t captra_mlp_pack_bytes(const captra_mlp_desc *d, int impl) {
     if (check_desc(d, "mlp_pack_bytes") != CAPTRA_OK) return -1;
     if (impl == 0) return (int64_t)(simt_layout(*d).total_floats * sizeof(float));
+    if (impl == 1) {
+        const int64_t n = tc_pack_bytes(d);
+        if (n < 0) set_error("mlp_pack_bytes: these layer widths are not covered by the tcgen05 path (use impl 0)");
+        return n;
+    }
     set_error("mlp_pack_bytes: impl %d not available", impl);
     return -1;
 }
@@ -27,6 +40,7 @@ extern "C" int captra_mlp_pack(const captra_mlp_desc *d, int impl, void *packed,
     CAPTRA_REQUIRE(packed && (reinterpret_cast<uintptr_t>(packed) & 15) == 0, "mlp_pack: packed buffer must be 16-byte aligned");
     for (int l = 0; l < d->nlayers; ++l) CAPTRA_REQUIRE(d->w[l], "mlp_pack: null weights for layer %d", l);
     if (impl == 0) return simt_pack(d, packed, as_stream(stream));
+    if (impl == 1) return tc_pack(d, packed, as_stream(stream));
     set_error("mlp_pack: impl %d not available", impl);
     return CAPTRA_ERR_UNSUPPORTED;
 }
@@ -44,6 +58,8 @@ extern "C" int captra_sa_mlp_max(int b, int n, int s, int k, int cfeat, const fl
     CAPTRA_REQUIRE((int64_t)b * n < (1LL << 31), "sa_mlp_max: b*n overflows int");
     if (impl == 0)
         return simt_sa_mlp_max(b, n, s, k, cfeat, xyz, new_xyz, feats, idx, d, packed, out, ldo, col_off, as_stream(stream));
+    if (impl == 1)
+        return tc_sa_mlp_max(b, n, s, k, cfeat, xyz, new_xyz, feats, idx, d, packed, out, ldo, col_off, as_stream(stream));
     set_error("sa_mlp_max: impl %d not available", impl);
     return CAPTRA_ERR_UNSUPPORTED;
 }
@@ -61,6 +77,10 @@ extern "C" int captra_point_mlp(int64_t rows, const float *segA, int64_t ldA, in
     CAPTRA_REQUIRE(packed && y && (segA || ca == 0) && (segB || cb == 0), "point_mlp: null pointer");
     if (impl == 0)
         return simt_point_mlp(rows, segA, ldA, ca, segB, ldB, cb, bcast_rows, d, packed, y, ldy, col_off, group, as_stream(stream));
+    if (impl == 1) {
+        CAPTRA_REQUIRE(group == 0, "point_mlp(tc): the grouped max is only available in impl 0");
+        return tc_point_mlp(rows, segA, ldA, ca, segB, ldB, cb, bcast_rows, d, packed, y, ldy, col_off, as_stream(stream));
+    }
     set_error("point_mlp: impl %d not available", impl);
     return CAPTRA_ERR_UNSUPPORTED;
 }

@@ -13,8 +13,8 @@ import torch
 from . import _lib
 
 MAX_LAYERS = 4
-# 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel.  CAPTRA_MLP_IMPL overrides.
-DEFAULT_IMPL = int(os.environ.get("CAPTRA_MLP_IMPL", "0"))
+# 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel (default).  CAPTRA_MLP_IMPL overrides.
+DEFAULT_IMPL = int(os.environ.get("CAPTRA_MLP_IMPL", "1"))
 
 
 class MlpDesc(ctypes.Structure):
@@ -39,7 +39,13 @@ def fold_conv_bn(conv, bn=None):
 
 
 class PackedMLP:
-    """A chain of up to 4 (linear + bias [+ ReLU]) layers with weights packed for one impl."""
+    """A chain of up to 4 (linear + bias [+ ReLU]) layers.  Weights are packed lazily per kernel
+    implementation; `impl` is the preferred one (1 = tcgen05 3xTF32) and the exact-fp32 CUDA-core
+    kernel (0) serves the shapes the tensor-core kernel does not cover (layers wider than 256,
+    nsample not in {32,64,128}, grouped max on dense rows).  Both are kernels of this library --
+    this is shape dispatch, not a fallback off the GPU."""
+
+    TC_GROUPS = (32, 64, 128)
 
     def __init__(self, weights, biases, relu_last=True, impl=None):
         assert 1 <= len(weights) <= MAX_LAYERS and len(weights) == len(biases)
@@ -49,29 +55,45 @@ class PackedMLP:
             raise _lib.CaptraError("PackedMLP: weights must live on a CUDA device (no CPU path)")
         self.cin = int(weights[0].shape[1])
         self.couts = [int(w.shape[0]) for w in weights]
+        self.relu_last = bool(relu_last)
+        self._w = [w.detach().to(torch.float32).contiguous() for w in weights]
+        self._b = [b.detach().to(torch.float32).contiguous() for b in biases]
+        for l, w in enumerate(self._w):
+            assert w.shape[1] == (self.cin if l == 0 else self.couts[l - 1]), "layer %d: cin mismatch" % l
         d = MlpDesc()
         d.nlayers, d.cin, d.relu_last = len(weights), self.cin, 1 if relu_last else 0
-        keep = []
-        for l, (w, b) in enumerate(zip(weights, biases)):
-            w = w.detach().to(torch.float32).contiguous()
-            b = b.detach().to(torch.float32).contiguous()
-            assert w.shape[1] == (self.cin if l == 0 else self.couts[l - 1]), "layer %d: cin mismatch" % l
-            keep += [w, b]
-            d.cout[l], d.w[l], d.bias[l] = self.couts[l], w.data_ptr(), b.data_ptr()
+        for l in range(len(weights)):
+            d.cout[l], d.w[l], d.bias[l] = self.couts[l], self._w[l].data_ptr(), self._b[l].data_ptr()
         self.desc = d
-        L = _lib.load()
-        nbytes = L.captra_mlp_pack_bytes(ctypes.byref(d), self.impl)
-        if nbytes < 0:
-            raise _lib.CaptraError("mlp_pack_bytes: " + L.captra_last_error().decode())
-        self.packed = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
-        _lib.check(L.captra_mlp_pack(ctypes.byref(d), self.impl, self.packed.data_ptr(),
-                                     _lib.stream_ptr(self.device)), "mlp_pack")
-        # the pack kernels read w/b asynchronously on the current stream; stream order keeps that
-        # safe as long as the tensors outlive the enqueue, which `keep` guarantees until here
-        torch.cuda.current_stream(self.device).synchronize()
-        for l in range(MAX_LAYERS):  # the execution calls never dereference these
-            d.w[l] = None
-            d.bias[l] = None
+        self._packs = {}
+        self._tc_ok = None
+        self._pack(self._pick(self.impl))
+
+    def _tc_supported(self):
+        if self._tc_ok is None:
+            self._tc_ok = _lib.load().captra_mlp_pack_bytes(ctypes.byref(self.desc), 1) >= 0
+        return self._tc_ok
+
+    def _pick(self, impl, group=0, sa=False):
+        if impl == 1 and self._tc_supported():
+            if sa and (group not in self.TC_GROUPS or not self.relu_last):
+                return 0
+            if not sa and group:
+                return 0
+            return 1
+        return 0
+
+    def _pack(self, impl):
+        if impl not in self._packs:
+            L = _lib.load()
+            nbytes = L.captra_mlp_pack_bytes(ctypes.byref(self.desc), impl)
+            if nbytes < 0:
+                raise _lib.CaptraError("mlp_pack_bytes: " + L.captra_last_error().decode())
+            buf = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            _lib.check(L.captra_mlp_pack(ctypes.byref(self.desc), impl, buf.data_ptr(),
+                                         _lib.stream_ptr(self.device)), "mlp_pack")
+            self._packs[impl] = buf
+        return self._packs[impl]
 
     @property
     def cout(self):
@@ -84,11 +106,12 @@ class PackedMLP:
         S, K = idx.shape[1], idx.shape[2]
         cfeat = 0 if feats is None else feats.shape[2]
         f32, i32 = torch.float32, torch.int32
-        _lib.call("sa_mlp_max[B=%d,N=%d,S=%d,K=%d,C=%d->%s]" % (B, N, S, K, cfeat + 3, "-".join(map(str, self.couts))),
+        impl = self._pick(self.impl, group=K, sa=True)
+        _lib.call("sa_mlp_max[B=%d,N=%d,S=%d,K=%d,C=%d->%s,impl=%d]" % (B, N, S, K, cfeat + 3, "-".join(map(str, self.couts)), impl),
                   _lib.load().captra_sa_mlp_max, B, N, S, K, cfeat, _lib.ptr(xyz, f32, "xyz"), _lib.ptr(new_xyz, f32, "new_xyz"),
-            _lib.ptr(feats, f32, "feats") if cfeat else None, _lib.ptr(idx, i32, "idx"),
-            ctypes.byref(self.desc), self.packed.data_ptr(), _lib.ptr(out, f32, "out"),
-            out.shape[-1], col_off, self.impl, _lib.stream_ptr(xyz.device), device=xyz.device)
+                  _lib.ptr(feats, f32, "feats") if cfeat else None, _lib.ptr(idx, i32, "idx"),
+                  ctypes.byref(self.desc), self._pack(impl).data_ptr(), _lib.ptr(out, f32, "out"),
+                  out.shape[-1], col_off, impl, _lib.stream_ptr(xyz.device), device=xyz.device)
         return out
 
     def rows(self, segA, segB=None, bcast_rows=0, group=0, out=None, col_off=0):
@@ -108,8 +131,9 @@ class PackedMLP:
         nout = R // group if group else R
         if out is None:
             out = torch.empty(nout, self.cout, dtype=f32, device=self.device)
-        _lib.call("point_mlp[R=%d,C=%d->%s,g=%d]" % (R, self.cin, "-".join(map(str, self.couts)), group),
-                  _lib.load().captra_point_mlp, R, pa, lda, ca, pb, ldb, cb, bcast_rows, ctypes.byref(self.desc), self.packed.data_ptr(),
-            _lib.ptr(out, f32, "out"), out.shape[-1], col_off, group, self.impl,
-            _lib.stream_ptr(self.device), device=self.device)
+        impl = self._pick(self.impl, group=group, sa=False)
+        _lib.call("point_mlp[R=%d,C=%d->%s,g=%d,impl=%d]" % (R, self.cin, "-".join(map(str, self.couts)), group, impl),
+                  _lib.load().captra_point_mlp, R, pa, lda, ca, pb, ldb, cb, bcast_rows, ctypes.byref(self.desc),
+                  self._pack(impl).data_ptr(), _lib.ptr(out, f32, "out"), out.shape[-1], col_off, group, impl,
+                  _lib.stream_ptr(self.device), device=self.device)
         return out

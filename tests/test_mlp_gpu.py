@@ -14,7 +14,7 @@ from captra_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 TOL = dict(rtol=1e-4, atol=1e-5)
-IMPLS = [0]
+IMPLS = [0, 1]
 
 
 @pytest.fixture(autouse=True)
@@ -123,8 +123,15 @@ def _golden_backbone(tag, cuda):
     return net.to(cuda).eval(), torch.from_numpy(g[tag + "/input"]).to(cuda), torch.from_numpy(g[tag + "/output"]).to(cuda)
 
 
+@pytest.fixture(params=IMPLS)
+def impl(request, monkeypatch):
+    from captra_b200 import mlp
+    monkeypatch.setattr(mlp, "DEFAULT_IMPL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("tag", ["coord", "rot"])
-def test_backbone_matches_reference_modules(tag, cuda):
+def test_backbone_matches_reference_modules(tag, impl, cuda):
     """The reference's own PointNet2Msg (torch Conv/BN, eval) produced tests/golden/backbone.npz;
     same weights through state_dict -> fused kernels must reproduce it."""
     net, x, want = _golden_backbone(tag, cuda)
@@ -152,7 +159,7 @@ def test_backbone_repacks_after_weight_update(cuda):
     torch.testing.assert_close(net(xg).detach(), y1, rtol=1e-4, atol=2e-5)
 
 
-def test_backbone_full_size_shapes(cuda):
+def test_backbone_full_size_shapes(impl, cuda):
     """BASELINE cfg2 shapes (pointnet2_camera.yml): B=4 here, 4096 points, both nets."""
     from captra_b200.backbones import PointNet2Msg
     from captra_b200.track import default_pointnet_cfg

@@ -19,8 +19,15 @@ def _cpu(d):
     return {k: v.detach().cpu() for k, v in d.items()}
 
 
+@pytest.fixture(params=[0, 1])
+def impl(request, monkeypatch):
+    from captra_b200 import mlp
+    monkeypatch.setattr(mlp, "DEFAULT_IMPL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("category,B", [("bottle", 3), ("laptop", 2)])
-def test_track_step_vs_cpu_restatement(category, B, cuda):
+def test_track_step_vs_cpu_restatement(category, B, impl, cuda):
     from captra_b200 import track
     from oracle import frame_ref
     cfg = track.make_cfg(category)
