@@ -17,7 +17,7 @@ int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const
                   float *out, int64_t ldo, int col_off, cudaStream_t stream);
 int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
                  int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
-                 cudaStream_t stream);
+                 int group, cudaStream_t stream);
 }  // namespace captra
 
 using namespace captra;
@@ -77,10 +77,8 @@ extern "C" int captra_point_mlp(int64_t rows, const float *segA, int64_t ldA, in
     CAPTRA_REQUIRE(packed && y && (segA || ca == 0) && (segB || cb == 0), "point_mlp: null pointer");
     if (impl == 0)
         return simt_point_mlp(rows, segA, ldA, ca, segB, ldB, cb, bcast_rows, d, packed, y, ldy, col_off, group, as_stream(stream));
-    if (impl == 1) {
-        CAPTRA_REQUIRE(group == 0, "point_mlp(tc): the grouped max is only available in impl 0");
-        return tc_point_mlp(rows, segA, ldA, ca, segB, ldB, cb, bcast_rows, d, packed, y, ldy, col_off, as_stream(stream));
-    }
+    if (impl == 1)
+        return tc_point_mlp(rows, segA, ldA, ca, segB, ldB, cb, bcast_rows, d, packed, y, ldy, col_off, group, as_stream(stream));
     set_error("point_mlp: impl %d not available", impl);
     return CAPTRA_ERR_UNSUPPORTED;
 }

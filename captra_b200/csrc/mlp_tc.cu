@@ -132,9 +132,10 @@ struct TcArgs {
     int n, s, cfeat; const float *xyz, *new_xyz, *feats; const int *idx;
     const float *segA; int64_t ldA; int ca; const float *segB; int64_t ldB; int cb; int bcast;
     int wstage_bytes, act_bytes, bias_floats;
+    int nsplit, last_npad, cout_total;          // single wide layer split into 256-column chunks over grid.y
 };
 
-template <int MODE>  // 0: SA gather + max, 1: dense rows
+template <int MODE>  // 0: SA gather loader, 1: dense-row loader; the last epilogue is chosen by a.group
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full_a[2], full_w[2], empty[2], d_ready;
@@ -148,6 +149,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+    // a single wide layer is split over grid.y: this CTA owns output columns [256*y, 256*y + npad)
+    int npad_y = 0, col_off = a.col_off, cout_last = a.cout_last;
+    const float *wpk0 = a.wpk[0], *bias0 = a.bias[0];
+    if (a.nsplit > 1) {
+        const int y = blockIdx.y;
+        npad_y = (y < a.nsplit - 1) ? 256 : a.last_npad;
+        wpk0 += (size_t)y * a.kpad[0] * 256 * 2;
+        bias0 += y * 256;
+        col_off += y * 256;
+        cout_last = min(256, a.cout_total - y * 256);
+    }
+    auto NPAD = [&](int l) { return a.nsplit > 1 ? npad_y : a.npad[l]; };
+    auto WPK = [&](int l) { return l == 0 ? wpk0 : a.wpk[l]; };
+    auto BIAS = [&](int l) { return l == 0 ? bias0 : a.bias[l]; };
+
     if (warp == 4) tmem_alloc<TC_TMEM_COLS>(&tmem_base_s);
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&full_a[i], 128); mbar_init(&full_w[i], 1); mbar_init(&empty[i], 1); }
@@ -157,8 +173,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
     {   // biases of all layers -> smem
         int off = 0;
         for (int l = 0; l < a.nlayers; ++l) {
-            for (int i = tid; i < a.npad[l]; i += TC_THREADS) bias_s[off + i] = __ldg(a.bias[l] + i);
-            off += a.npad[l];
+            for (int i = tid; i < NPAD(l); i += TC_THREADS) bias_s[off + i] = __ldg(BIAS(l) + i);
+            off += NPAD(l);
         }
     }
     tcgen05_fence_before();
@@ -172,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             for (int l = 0; l < a.nlayers; ++l) {
                 const int nslab = a.kpad[l] / TC_KC;
-                const uint32_t npad = (uint32_t)a.npad[l];
+                const uint32_t npad = (uint32_t)NPAD(l);
                 const uint32_t idesc = make_idesc(2, TC_ROWS, (int)npad);
                 const uint32_t b_lbo = npad * 16, b_lo_off = 4 * npad * 16;
                 for (int s = 0; s < nslab; ++s, ++it) {
@@ -204,13 +220,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             for (int l = 0; l < a.nlayers; ++l) {
                 const int nslab = a.kpad[l] / TC_KC;
-                const uint32_t bytes = 2u * 4u * (uint32_t)a.npad[l] * 16u;
+                const uint32_t bytes = 2u * 4u * (uint32_t)NPAD(l) * 16u;
                 for (int s = 0; s < nslab; ++s, ++it) {
                     const uint32_t st = it & 1, ph = (it >> 1) & 1;
                     mbar_wait(&empty[st], ph ^ 1);
                     mbar_arrive_expect_tx(&full_w[st], bytes);
                     bulk_g2s(w_stage + (size_t)st * a.wstage_bytes,
-                             reinterpret_cast<const uint8_t *>(a.wpk[l]) + (size_t)s * bytes, bytes, &full_w[st]);
+                             reinterpret_cast<const uint8_t *>(WPK(l)) + (size_t)s * bytes, bytes, &full_w[st]);
                 }
             }
         }
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
                 tcgen05_fence_after();
                 const bool last = l == a.nlayers - 1;
                 const bool relu = !last || a.relu_last;
-                const int npad = a.npad[l];
+                const int npad = NPAD(l);
                 const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
                 for (int c0 = 0; c0 < npad; c0 += 16) {
                     uint32_t v[16];
@@ -328,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
                         for (int q = 0; q < 4; ++q)
                             *reinterpret_cast<float4 *>(act + (size_t)(c0 / 4 + q) * (TC_ROWS * 4) + r * 4) =
                                 make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-                    } else if (MODE == 0) {
+                    } else if (a.group > 0) {
                         // max over the 32 rows of this warp, column by column; lane j keeps column c0+j
                         uint32_t keep = 0;
 #pragma unroll
@@ -338,19 +354,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
                         }
                         if (lane < 16) red[warp * 256 + c0 + lane] = __uint_as_float(keep);
                     } else if (valid) {
-                        float *dst = a.out + grow * a.ldo + a.col_off + c0;
-                        if (c0 + 16 <= a.cout_last && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                        float *dst = a.out + grow * a.ldo + col_off + c0;
+                        if (c0 + 16 <= cout_last && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
                                 *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
-                                if (c0 + j < a.cout_last) dst[j] = x[j];
+                                if (c0 + j < cout_last) dst[j] = x[j];
                         }
                     }
                 }
-                if (last && MODE == 0) {
+                if (last && a.group > 0) {
                     // combine the per-warp maxima of the warps that share a centroid and write it out
                     const int wpg = a.group / 32;                 // warps per centroid: 1, 2 or 4
                     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -358,10 +374,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
                     for (int o = tid; o < ngroups * npad; o += 128) {
                         const int g = o / npad, c = o - g * npad;
                         const int64_t cen = (tile * TC_ROWS) / a.group + g;
-                        if (c >= a.cout_last || cen * a.group >= a.rows) continue;
+                        if (c >= cout_last || cen * a.group >= a.rows) continue;
                         float m = red[(g * wpg) * 256 + c];
                         for (int w = 1; w < wpg; ++w) m = fmaxf(m, red[(g * wpg + w) * 256 + c]);
-                        a.out[cen * a.ldo + a.col_off + c] = m;
+                        a.out[cen * a.ldo + col_off + c] = m;
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
@@ -402,7 +418,7 @@ __global__ void pack_tc_kernel(int cin, int cout, int kpad, int npad, const floa
 struct TcLayout {
     int nlayers, kpad[CAPTRA_MAX_MLP_LAYERS], npad[CAPTRA_MAX_MLP_LAYERS];
     size_t off_w[CAPTRA_MAX_MLP_LAYERS], off_b[CAPTRA_MAX_MLP_LAYERS], total_floats;
-    int wstage_bytes, act_bytes, bias_floats;
+    int wstage_bytes, act_bytes, bias_floats, nsplit, last_npad;
     size_t smem_bytes;
     bool supported;
 };
@@ -413,11 +429,19 @@ static TcLayout tc_layout(const captra_mlp_desc &d) {
     L.supported = true;
     size_t off = 0;
     int cin = d.cin, npmax = 16, actmax = 0;
+    L.nsplit = 1;
     for (int l = 0; l < d.nlayers; ++l) {
         L.kpad[l] = round_up(cin, TC_KC);
         L.npad[l] = round_up(d.cout[l], 16);
-        if (L.npad[l] > 256) L.supported = false;
-        npmax = max(npmax, L.npad[l]);
+        if (L.npad[l] > 256) {
+            if (d.nlayers == 1) {   // one wide layer: 256-column chunks over grid.y
+                L.nsplit = ceil_div(L.npad[l], 256);
+                L.last_npad = L.npad[l] - 256 * (L.nsplit - 1);
+            } else {
+                L.supported = false;
+            }
+        }
+        npmax = max(npmax, min(L.npad[l], 256));
         if (l < d.nlayers - 1) actmax = max(actmax, L.npad[l]);
         L.off_w[l] = off; off += (size_t)L.kpad[l] * L.npad[l] * 2;
         L.off_b[l] = off; off += L.npad[l];
@@ -445,9 +469,15 @@ int tc_pack(const captra_mlp_desc *d, void *packed, cudaStream_t stream) {
     int cin = d->cin;
     for (int l = 0; l < d->nlayers; ++l) {
         float *base = reinterpret_cast<float *>(packed);
-        pack_tc_kernel<<<64, 256, 0, stream>>>(cin, d->cout[l], L.kpad[l], L.npad[l], d->w[l], d->bias[l],
-                                               base + L.off_w[l], base + L.off_b[l]);
-        CAPTRA_CHECK_LAUNCH("mlp_pack(tc)");
+        for (int y = 0; y < L.nsplit; ++y) {   // nsplit > 1 only for a single wide layer
+            const int npad_y = L.nsplit == 1 ? L.npad[l] : (y < L.nsplit - 1 ? 256 : L.last_npad);
+            const int cout_y = L.nsplit == 1 ? d->cout[l] : min(256, d->cout[l] - 256 * y);
+            pack_tc_kernel<<<64, 256, 0, stream>>>(cin, cout_y, L.kpad[l], npad_y, d->w[l] + (size_t)y * 256 * cin,
+                                                   d->bias[l] ? d->bias[l] + y * 256 : nullptr,
+                                                   base + L.off_w[l] + (size_t)y * L.kpad[l] * 256 * 2,
+                                                   base + L.off_b[l] + y * 256);
+            CAPTRA_CHECK_LAUNCH("mlp_pack(tc)");
+        }
         cin = d->cout[l];
     }
     return CAPTRA_OK;
@@ -463,6 +493,7 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, size
         a.bias[l] = reinterpret_cast<const float *>(packed) + L.off_b[l];
     }
     a.wstage_bytes = L.wstage_bytes; a.act_bytes = L.act_bytes; a.bias_floats = L.bias_floats;
+    a.nsplit = L.nsplit; a.last_npad = L.last_npad; a.cout_total = d->cout[d->nlayers - 1];
     *smem = L.smem_bytes;
     return CAPTRA_OK;
 }
@@ -472,9 +503,9 @@ static int tc_launch(TcArgs &a, size_t smem, cudaStream_t stream) {
     auto kern = mlp_tc_kernel<MODE>;
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
-    const int nsm = sm_count();
-    const int grid = a.ntiles < nsm ? (int)a.ntiles : nsm;
-    kern<<<grid, TC_THREADS, smem, stream>>>(a);
+    const int nsm = max(1, sm_count() / a.nsplit);
+    const int gx = a.ntiles < nsm ? (int)a.ntiles : nsm;
+    kern<<<dim3(gx, a.nsplit), TC_THREADS, smem, stream>>>(a);
     CAPTRA_CHECK_LAUNCH("mlp_tc");
     return CAPTRA_OK;
 }
@@ -496,12 +527,14 @@ int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const
 
 int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
                  int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
-                 cudaStream_t stream) {
+                 int group, cudaStream_t stream) {
+    CAPTRA_REQUIRE(group == 0 || ((group == 32 || group == 64 || group == 128) && d->relu_last),
+                   "point_mlp(tc): grouped max needs group in {32,64,128} and a final ReLU");
     TcArgs a{};
     size_t smem;
     int rc = tc_fill(a, d, packed, &smem);
     if (rc) return rc;
-    a.rows = rows; a.group = 0;
+    a.rows = rows; a.group = group;
     a.out = y; a.ldo = ldy; a.col_off = col_off;
     a.segA = segA; a.ldA = ldA; a.ca = ca; a.segB = segB; a.ldB = ldB; a.cb = cb; a.bcast = bcast;
     return tc_launch<1>(a, smem, stream);

@@ -67,7 +67,17 @@ class PackedMLP:
         self.desc = d
         self._packs = {}
         self._tc_ok = None
-        self._pack(self._pick(self.impl))
+        # Chains the fused tensor-core kernel cannot hold on chip (a layer wider than 256 columns, or
+        # activations + weight stages beyond 227 KB of shared memory: sa3, fp3, fp2) run layer by layer
+        # on the same tcgen05 kernel, a wide layer split into 256-column chunks over grid.y; the
+        # [rows, cout] intermediates are a few MB and stay in L2.
+        self._layers = None
+        if self.impl == 1 and len(weights) > 1 and not self._tc_supported():
+            n = len(weights)
+            self._layers = [PackedMLP([self._w[l]], [self._b[l]], relu_last=(l < n - 1 or self.relu_last), impl=1)
+                            for l in range(n)]
+        else:
+            self._pack(self._pick(self.impl))
 
     def _tc_supported(self):
         if self._tc_ok is None:
@@ -78,7 +88,7 @@ class PackedMLP:
         if impl == 1 and self._tc_supported():
             if sa and (group not in self.TC_GROUPS or not self.relu_last):
                 return 0
-            if not sa and group:
+            if not sa and group and (group not in self.TC_GROUPS or not self.relu_last):
                 return 0
             return 1
         return 0
@@ -106,7 +116,7 @@ class PackedMLP:
         S, K = idx.shape[1], idx.shape[2]
         cfeat = 0 if feats is None else feats.shape[2]
         f32, i32 = torch.float32, torch.int32
-        impl = self._pick(self.impl, group=K, sa=True)
+        impl = 0 if self._layers is not None else self._pick(self.impl, group=K, sa=True)
         _lib.call("sa_mlp_max[B=%d,N=%d,S=%d,K=%d,C=%d->%s,impl=%d]" % (B, N, S, K, cfeat + 3, "-".join(map(str, self.couts)), impl),
                   _lib.load().captra_sa_mlp_max, B, N, S, K, cfeat, _lib.ptr(xyz, f32, "xyz"), _lib.ptr(new_xyz, f32, "new_xyz"),
                   _lib.ptr(feats, f32, "feats") if cfeat else None, _lib.ptr(idx, i32, "idx"),
@@ -125,6 +135,11 @@ class PackedMLP:
             if not (t.is_cuda and t.dtype == f32 and t.dim() == 2 and t.stride(1) == 1):
                 raise _lib.CaptraError("%s must be a CUDA fp32 [rows, ch] tensor with contiguous channels" % name)
             return t.data_ptr(), t.stride(0), t.shape[1]
+        if self._layers is not None:
+            x = self._layers[0].rows(segA, segB, bcast_rows=bcast_rows)
+            for layer in self._layers[1:-1]:
+                x = layer.rows(x)
+            return self._layers[-1].rows(x, group=group, out=out, col_off=col_off)
         pa, lda, ca = seg(segA, "segA")
         pb, ldb, cb = seg(segB, "segB")
         R = segA.shape[0] if segA is not None else (segB.shape[0] * max(bcast_rows, 1))

@@ -43,12 +43,21 @@ def test_track_step_vs_cpu_restatement(category, B, impl, cuda):
     canon = {k: pose[k][:, trk.root].to(cuda) for k in ("rotation", "translation", "scale")}
     from captra_b200.networks import canonicalize
     with torch.no_grad():
-        feat = trk.npcs_net.backbone(canonicalize(pts.to(cuda), mean.to(cuda), canon))
-    torch.testing.assert_close(feat.cpu(), inter["feat"], rtol=2e-4, atol=2e-5)
+        cam = canonicalize(pts.to(cuda), mean.to(cuda), canon)
+        feat = trk.npcs_net.backbone(cam)
+        labels = torch.max(torch.softmax(trk.npcs_net.seg_head(feat), dim=1), dim=-2)[1]
+    # impl 0 is exact fp32 (summation order only); impl 1 is 3xTF32: ~2^-21 per product, which after
+    # ~19 layers with cancellation shows up as ~1e-4 absolute on O(1) features
+    ftol = dict(rtol=2e-4, atol=2e-5) if impl == 0 else dict(rtol=1e-3, atol=2e-4)
+    torch.testing.assert_close(feat.cpu(), inter["feat"], **ftol)
+    flips = (labels.cpu() != inter["labels"]).float().mean().item()
+    assert flips < 1e-3, "argmax labels differ on %.4f of the points" % flips
     assert got["translation"].shape == want["translation"].shape == (B, cfg["num_parts"], 3, 1)
+    # north-star bar: fp32 pose within 1e-4 relative (|t| ~ 1 m, s ~ 0.2-0.5)
     torch.testing.assert_close(got["rotation"].cpu(), want["rotation"], rtol=1e-4, atol=2e-5)
-    torch.testing.assert_close(got["scale"].cpu(), want["scale"], rtol=1e-3, atol=1e-5)
-    torch.testing.assert_close(got["translation"].cpu(), want["translation"], rtol=1e-3, atol=1e-4)
+    stol = dict(rtol=1e-4, atol=1e-5) if flips == 0 else dict(rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(got["scale"].cpu(), want["scale"], **stol)
+    torch.testing.assert_close(got["translation"].cpu(), want["translation"], rtol=stol["rtol"], atol=1e-4)
     for k in got:
         assert torch.isfinite(got[k]).all()
 
