@@ -6,6 +6,7 @@
 #include "tc_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace captra {
 using namespace tc;
@@ -94,58 +95,96 @@ __global__ void __launch_bounds__(128) umma_debug_gemm_kernel(int K, int N, cons
 // ------------------------------------------------------------------------------------------------
 // The fused kernel.
 //
-// One persistent CTA per SM walks 128-row tiles.  Warps 0-3 ("row threads", thread r <-> tile row r
-// <-> TMEM lane r) produce the A operand and run the epilogues; warp 4 (one elected thread) issues
+// Persistent CTAs walk 128-row tiles.  Warps 0-3 ("row threads", thread r <-> tile row r <-> TMEM
+// lane r) produce the A operand and run the epilogues; warp 4 (one elected thread) issues
 // tcgen05.mma; warp 5 (one elected thread) streams the pre-split weights with bulk-copy TMA.
 //
-//   layer l, K slab s (16 input channels):
-//     row threads : A slab -> (hi, lo) planes of a_stage[s & 1]
-//                   layer 0: gathered from global through the index list (SA) / row pointers (dense)
-//                   layer>0: split from the fp32 activation plane kept in shared memory
-//     TMA thread  : W slab (hi plane | lo plane, already split and chunk-major in global) -> w_stage[s & 1]
-//     MMA thread  : 2 k-steps x 3 terms (lo*hi, hi*lo, hi*hi) of tcgen05.mma kind::tf32 into TMEM,
-//                   tcgen05.commit -> empty[s & 1]; after the last slab also -> d_ready
-//   epilogue l   : row threads tcgen05.ld their lane, + bias, ReLU, then
-//                   l < last : write the fp32 activation plane (chunk-major, same addressing as the
-//                              operand planes, so thread r only ever touches row r: no CTA barrier)
-//                   l = last : SA   -> max over the K rows of each centroid by redux.sync on the
-//                                      (non-negative) float bit patterns, one coalesced row write
-//                              dense-> the thread's row straight to global (point-major)
+//   layer l, K slab s (16 input channels), stage st = slab counter mod NST:
+//     row threads : A slab -> (hi, lo) planes of a_stage[st]
+//         layer 0 : gathered from global through the index list (SA) or row pointers (dense), with a
+//                   3-slab register prefetch so the L2 gather latency hides behind the MMAs
+//         layer>0 : read straight out of TMEM -- 16 accumulator columns of layer l-1 ARE slab s of
+//                   layer l -- + bias, ReLU, 3xTF32 split.  The epilogue of layer l-1 and the MMAs
+//                   of layer l therefore overlap slab by slab; accumulators ping-pong between two
+//                   TMEM regions and no activation ever touches shared memory in fp32.
+//     TMA thread  : W slab (hi plane | lo plane, pre-split, chunk-major in global) -> w_stage[st]
+//     MMA thread  : 2 k-steps x 3 terms (lo*hi, hi*lo, hi*hi) of tcgen05.mma kind::tf32,
+//                   tcgen05.commit -> empty[st]; after a layer's last slab also -> d_ready
+//   last epilogue : group > 0 -> max over the rows of each group by redux.sync on the (non-negative)
+//                                float bit patterns, one coalesced row write per group
+//                   group = 0 -> the thread's row straight to global (point-major)
 //
 // Shared-memory operand layout (K-major, no swizzle): element (row, k) of a 16-channel slab lives at
-//   plane + (k/4) * ROWS*16 + row*16 + (k%4)*4      -> LBO = ROWS*16, SBO = 128 in the descriptors.
+//   plane + (k/4) * ROWS*16 + row*16 + (k%4)*4      -> LBO = ROWS*16, SBO = 128 in the descriptors,
+// so thread r writes 16-byte pieces at r*16 (conflict-free) and never touches another row.
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 192;
-constexpr int TC_KC = 16;                         // channels per slab
-constexpr int TC_A_PLANE = 4 * TC_CHUNK_BYTES;    // bytes of one (hi or lo) A slab plane: 8 KB
+constexpr int TC_GROUPS = 2;                      // producer groups; group g owns every 2nd slab
+constexpr int TC_PROD = 128 * TC_GROUPS;          // producer / epilogue threads (warps 0-7)
+constexpr int TC_THREADS = TC_PROD + 64;          // + MMA warp (8) + TMA warp (9)
+constexpr int TC_KC = 32;                         // channels per slab (8 chunks of 16 bytes, 4 k-steps of 8)
+constexpr int TC_NCHUNK = TC_KC / 4;
+constexpr int TC_A_PLANE = TC_NCHUNK * TC_CHUNK_BYTES;   // bytes of one (hi or lo) A slab plane: 16 KB
 constexpr int TC_A_STAGE = 2 * TC_A_PLANE;        // hi + lo
-constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_MAX_STAGES = 4;
 
 struct TcArgs {
     int nlayers, relu_last, cout_last;
     int kpad[CAPTRA_MAX_MLP_LAYERS], npad[CAPTRA_MAX_MLP_LAYERS];
-    const float *wpk[CAPTRA_MAX_MLP_LAYERS];   // [nslab][2 planes][4 chunks][npad][4]
+    const float *wpk[CAPTRA_MAX_MLP_LAYERS];   // [nslab][2 planes][8 chunks][npad][4]
     const float *bias[CAPTRA_MAX_MLP_LAYERS];  // [npad]
     int64_t rows, ntiles;
-    int group;                                  // SA: nsample (32|64|128); dense: 0
+    int group;                                  // max over each `group` rows (32|64|128) or 0
     float *out; int64_t ldo; int col_off;
     int n, s, cfeat; const float *xyz, *new_xyz, *feats; const int *idx;
     const float *segA; int64_t ldA; int ca; const float *segB; int64_t ldB; int cb; int bcast;
-    int wstage_bytes, act_bytes, bias_floats;
+    int wstage_bytes, bias_floats, region_cols, tmem_cols, nst_log2;
     int nsplit, last_npad, cout_total;          // single wide layer split into 256-column chunks over grid.y
+    int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A stores, 2 no W copies, 4 no MMAs, 8 no last epilogue, 32/128 stamps, 64 no gather
 };
 
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t *smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// timing probe: producer thread 0 of CTA 0 stamps clock64() at phase boundaries of its first tiles
+__device__ long long g_tc_ts[512];
+__device__ int g_tc_ts_n;
+#define TC_STAMP_T(code, T)                                                         \
+    do {                                                                            \
+        if ((a.dbg & (T)) && blockIdx.x == 0 && blockIdx.y == 0) {                  \
+            const int i__ = g_tc_ts_n;                                              \
+            if (i__ < 255) { g_tc_ts[2 * i__] = clock64(); g_tc_ts[2 * i__ + 1] = (code); g_tc_ts_n = i__ + 1; } \
+        }                                                                           \
+    } while (0)
+#define TC_STAMP(code)                                                              \
+    do {                                                                            \
+        if ((a.dbg & 32) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {       \
+            const int i__ = g_tc_ts_n;                                              \
+            if (i__ < 255) { g_tc_ts[2 * i__] = clock64(); g_tc_ts[2 * i__ + 1] = (code); g_tc_ts_n = i__ + 1; } \
+        }                                                                           \
+    } while (0)
+
+// What bounds this kernel (clock64 probes, profiles/r01_tc_probe.txt): the single MMA-issuing thread.
+// One tcgen05.mma costs it ~80 cycles to issue and one barrier round (two try_waits + commit) ~450,
+// while a kind::tf32 MMA of N=128 is only 64 tensor-pipe cycles.  Hence: 32-channel slabs (12 MMAs
+// per barrier round), ONE `full` barrier per stage shared by the A producers and the weight TMA
+// (4 warp arrivals + 1 arrive.expect_tx), descriptors advanced by adding to their low word, and
+// two producer groups that alternate slabs so their per-slab latency chains overlap.
 template <int MODE>  // 0: SA gather loader, 1: dense-row loader; the last epilogue is chosen by a.group
-__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t full_a[2], full_w[2], empty[2], d_ready;
+    __shared__ uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], d_ready;
     __shared__ uint32_t tmem_base_s;
 
-    uint8_t *a_stage = smem_raw;                                   // 2 x TC_A_STAGE
-    uint8_t *w_stage = a_stage + 2 * TC_A_STAGE;                   // 2 x wstage_bytes
-    float *act = reinterpret_cast<float *>(w_stage + 2 * (size_t)a.wstage_bytes);
-    float *bias_s = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(act) + a.act_bytes);
-    float *red = bias_s + a.bias_floats;                           // [4][256]
+    const uint32_t nst_log2 = (uint32_t)a.nst_log2, NST = 1u << nst_log2;
+    uint8_t *a_stage = smem_raw;                                          // NST x TC_A_STAGE
+    uint8_t *w_stage = a_stage + (size_t)NST * TC_A_STAGE;                // NST x wstage_bytes
+    float *bias_s = reinterpret_cast<float *>(w_stage + (size_t)NST * a.wstage_bytes);
+    float *red = reinterpret_cast<float *>(a_stage);                      // [4][256], aliases stage 0 (idle in the last epilogue)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -164,9 +203,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
     auto WPK = [&](int l) { return l == 0 ? wpk0 : a.wpk[l]; };
     auto BIAS = [&](int l) { return l == 0 ? bias0 : a.bias[l]; };
 
-    if (warp == 4) tmem_alloc<TC_TMEM_COLS>(&tmem_base_s);
+    if (warp == TC_PROD / 32) tmem_alloc_dyn(&tmem_base_s, (uint32_t)a.tmem_cols);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&full_a[i], 128); mbar_init(&full_w[i], 1); mbar_init(&empty[i], 1); }
+        for (uint32_t i = 0; i < NST; ++i) { mbar_init(&full[i], 4 + 1); mbar_init(&empty[i], 1); }
         mbar_init(&d_ready, 1);
         fence_mbar_init();
     }
@@ -180,65 +219,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_d = tmem_base_s;
+    const uint32_t tmem_base = tmem_base_s;
 
-    if (tid == 128) {
+    if (tid == TC_PROD) {
         // ===================== MMA issuer =====================
         uint32_t it = 0;
+        const uint64_t a_desc0 = smem_desc_kmajor_noswz(smem_u32(a_stage), TC_CHUNK_BYTES, 128);
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             for (int l = 0; l < a.nlayers; ++l) {
                 const int nslab = a.kpad[l] / TC_KC;
                 const uint32_t npad = (uint32_t)NPAD(l);
                 const uint32_t idesc = make_idesc(2, TC_ROWS, (int)npad);
-                const uint32_t b_lbo = npad * 16, b_lo_off = 4 * npad * 16;
+                const uint32_t b_lbo = npad * 16;
+                const uint64_t b_desc0 = smem_desc_kmajor_noswz(smem_u32(w_stage), b_lbo, 128);
+                const uint32_t b_lo_off = (TC_NCHUNK * b_lbo) >> 4, b_step = (2 * b_lbo) >> 4;   // in 16-byte units
+                const uint32_t tmem_d = tmem_base + (uint32_t)((l & 1) * a.region_cols);
                 for (int s = 0; s < nslab; ++s, ++it) {
-                    const uint32_t st = it & 1, ph = (it >> 1) & 1;
-                    mbar_wait(&full_a[st], ph);
-                    mbar_wait(&full_w[st], ph);
+                    const uint32_t st = it & (NST - 1), ph = (it >> nst_log2) & 1;
+                    TC_STAMP_T(40, 128);
+                    mbar_wait(&full[st], ph);
                     tcgen05_fence_after();
-                    const uint32_t abase = smem_u32(a_stage + st * TC_A_STAGE);
-                    const uint32_t bbase = smem_u32(w_stage + (size_t)st * a.wstage_bytes);
+                    TC_STAMP_T(42, 128);
+                    // descriptors of this stage: only the 14-bit start-address field (16-byte units) moves
+                    uint64_t ah = a_desc0 + (uint64_t)((st * TC_A_STAGE) >> 4);
+                    uint64_t al = ah + (TC_A_PLANE >> 4);
+                    uint64_t bh = b_desc0 + (uint64_t)((st * (uint32_t)a.wstage_bytes) >> 4);
+                    uint64_t bl = bh + b_lo_off;
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint32_t ao = (uint32_t)(2 * j) * TC_CHUNK_BYTES, bo = (uint32_t)(2 * j) * b_lbo;
-                        const uint64_t ah = smem_desc_kmajor_noswz(abase + ao, TC_CHUNK_BYTES, 128);
-                        const uint64_t al = smem_desc_kmajor_noswz(abase + TC_A_PLANE + ao, TC_CHUNK_BYTES, 128);
-                        const uint64_t bh = smem_desc_kmajor_noswz(bbase + bo, b_lbo, 128);
-                        const uint64_t bl = smem_desc_kmajor_noswz(bbase + b_lo_off + bo, b_lbo, 128);
+                    for (int j = 0; j < TC_KC / 8; ++j) {
+                        if (a.dbg & 4) break;
                         umma_tf32(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
                         umma_tf32(tmem_d, ah, bl, idesc, 1u);
                         umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                        ah += (2 * TC_CHUNK_BYTES) >> 4; al += (2 * TC_CHUNK_BYTES) >> 4;
+                        bh += b_step; bl += b_step;
                     }
+                    TC_STAMP_T(43, 128);
                     umma_commit(&empty[st]);
                     if (s == nslab - 1) umma_commit(&d_ready);
                 }
             }
         }
-    } else if (tid == 160) {
+    } else if (tid == TC_PROD + 32) {
         // ===================== weight producer (bulk-copy TMA) =====================
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             for (int l = 0; l < a.nlayers; ++l) {
                 const int nslab = a.kpad[l] / TC_KC;
-                const uint32_t bytes = 2u * 4u * (uint32_t)NPAD(l) * 16u;
+                const uint32_t bytes = 2u * TC_NCHUNK * (uint32_t)NPAD(l) * 16u;
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(WPK(l));
                 for (int s = 0; s < nslab; ++s, ++it) {
-                    const uint32_t st = it & 1, ph = (it >> 1) & 1;
+                    const uint32_t st = it & (NST - 1), ph = (it >> nst_log2) & 1;
                     mbar_wait(&empty[st], ph ^ 1);
-                    mbar_arrive_expect_tx(&full_w[st], bytes);
-                    bulk_g2s(w_stage + (size_t)st * a.wstage_bytes,
-                             reinterpret_cast<const uint8_t *>(WPK(l)) + (size_t)s * bytes, bytes, &full_w[st]);
+                    if (a.dbg & 2) {
+                        mbar_arrive(&full[st]);
+                    } else {
+                        mbar_arrive_expect_tx(&full[st], bytes);
+                        bulk_g2s(w_stage + (size_t)st * a.wstage_bytes, src + (size_t)s * bytes, bytes, &full[st]);
+                    }
                 }
             }
         }
-    } else if (tid < 128) {
-        // ===================== row threads: A producer + epilogue =====================
-        const int r = tid;
-        uint32_t it = 0, dl = 0;
+    } else if (tid < TC_PROD) {
+        // ===================== producer / epilogue threads =====================
+        const int r = tid & 127;              // tile row == TMEM lane
+        const int g = tid >> 7;               // producer group
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        uint32_t base = 0;                    // global index of the current layer's slab 0
+        uint32_t dl = 0;
+
+        auto warp_wait = [&](uint64_t *bar, uint32_t parity) {   // one lane polls, the warp follows
+            if (lane == 0) mbar_wait(bar, parity);
+            __syncwarp();
+        };
+        // store 16 channels (half a slab: chunks 4*half .. 4*half+3) of global slab `it` as hi/lo planes
+        auto store_half = [&](uint32_t it, int half, const float4 (&v)[4]) {
+            const uint32_t st = it & (NST - 1);
+            float *hi = reinterpret_cast<float *>(a_stage + st * TC_A_STAGE) + (4 * half) * (TC_ROWS * 4) + r * 4;
+            float *lo = hi + TC_A_PLANE / 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (a.dbg & 1) break;
+                float4 hh, ll;
+                split_tf32(v[q].x, hh.x, ll.x); split_tf32(v[q].y, hh.y, ll.y);
+                split_tf32(v[q].z, hh.z, ll.z); split_tf32(v[q].w, hh.w, ll.w);
+                *reinterpret_cast<float4 *>(hi + q * (TC_ROWS * 4)) = hh;
+                *reinterpret_cast<float4 *>(lo + q * (TC_ROWS * 4)) = ll;
+            }
+        };
+        auto acquire = [&](uint32_t it) {     // wait until the MMAs that last read this slab's stage are done
+            warp_wait(&empty[it & (NST - 1)], ((it >> nst_log2) & 1) ^ 1);
+        };
+        auto release = [&](uint32_t it) {     // hand the filled stage to the MMA thread
+            // every writer fences its own generic-proxy stores towards the async proxy; one elected
+            // lane per warp then arrives
+            fence_proxy_async_smem();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[it & (NST - 1)]);
+        };
+
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int64_t grow = tile * TC_ROWS + r;
             const bool valid = grow < a.rows;
+            TC_STAMP(0);
             // ---- per-row metadata
-            const float *frow = nullptr;   // SA: feature row of the gathered point
+            const float *frow = nullptr;         // SA: feature row of the gathered point
             float px = 0.f, py = 0.f, pz = 0.f;  // SA: point - centroid
             const float *arow = nullptr, *brow = nullptr;
             if (valid) {
@@ -255,8 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
                     brow = a.segB ? a.segB + (a.bcast ? grow / a.bcast : grow) * a.ldB : nullptr;
                 }
             }
-            // layer-0 input element c of this row
-            auto in0 = [&](int c) -> float {
+            auto in0 = [&](int c) -> float {     // layer-0 input element c of this row
                 if (!valid) return 0.f;
                 if (MODE == 0) {
                     if (c < a.cfeat) return __ldg(frow + c);
@@ -268,83 +353,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
                     return 0.f;
                 }
             };
-            auto load_slab0 = [&](int s, float4 (&v)[4]) {
-                const int c0 = s * TC_KC;
-                const int nvec = MODE == 0 ? a.cfeat : a.ca;       // leading segment length
-                const float *base = MODE == 0 ? frow : arow;
-                const bool vec_ok = valid && base && (c0 + TC_KC <= nvec) &&
-                                    ((reinterpret_cast<uintptr_t>(base + c0) & 15) == 0);
-                if (vec_ok) {
+            const int nvec = MODE == 0 ? a.cfeat : a.ca;           // leading segment length
+            const float *vbase = MODE == 0 ? frow : arow;
+            const bool vec_row = valid && vbase && ((reinterpret_cast<uintptr_t>(vbase) & 15) == 0);
+            auto load16 = [&](int c0, float4 (&v)[4]) {             // 16 consecutive layer-0 channels
+                if (a.dbg & 64) {   // probe: no global gather
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(base + c0) + q);
+                    for (int q = 0; q < 4; ++q) v[q] = make_float4(px, py, pz, 1.f);
+                    return;
+                }
+                if (vec_row && c0 + 16 <= nvec) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(vbase + c0) + q);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         v[q] = make_float4(in0(c0 + 4 * q), in0(c0 + 4 * q + 1), in0(c0 + 4 * q + 2), in0(c0 + 4 * q + 3));
                 }
             };
-            auto store_slab = [&](uint32_t st, const float4 (&v)[4]) {
-                float *hi = reinterpret_cast<float *>(a_stage + st * TC_A_STAGE);
-                float *lo = reinterpret_cast<float *>(a_stage + st * TC_A_STAGE + TC_A_PLANE);
+            TC_STAMP(1);
+            // ---------------- layer 0: this group's slabs, the next one prefetched ----------------
+            {
+                const int nslab = a.kpad[0] / TC_KC;
+                int s = (int)((g - base) & (TC_GROUPS - 1));      // first slab of this layer owned by group g
+                float4 c0v[4], c1v[4], n0v[4], n1v[4];
+                if (s < nslab) { load16(s * TC_KC, c0v); load16(s * TC_KC + 16, c1v); }
+                for (; s < nslab; s += TC_GROUPS) {
+                    const bool more = s + TC_GROUPS < nslab;
+                    if (more) { load16((s + TC_GROUPS) * TC_KC, n0v); load16((s + TC_GROUPS) * TC_KC + 16, n1v); }
+                    acquire(base + s);
+                    store_half(base + s, 0, c0v);
+                    store_half(base + s, 1, c1v);
+                    release(base + s);
+                    if (more) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 h, l;
-                    split_tf32(v[q].x, h.x, l.x); split_tf32(v[q].y, h.y, l.y);
-                    split_tf32(v[q].z, h.z, l.z); split_tf32(v[q].w, h.w, l.w);
-                    *reinterpret_cast<float4 *>(hi + q * (TC_ROWS * 4) + r * 4) = h;
-                    *reinterpret_cast<float4 *>(lo + q * (TC_ROWS * 4) + r * 4) = l;
+                        for (int q = 0; q < 4; ++q) { c0v[q] = n0v[q]; c1v[q] = n1v[q]; }
+                    }
                 }
-            };
-
+                base += nslab;
+            }
+            TC_STAMP(2);
+            // ---------------- layers 1..L-1: previous accumulator -> next operand ----------------
             int bias_off = 0;
-            for (int l = 0; l < a.nlayers; ++l) {
-                const int nslab = a.kpad[l] / TC_KC;
-                // ---------------- produce the A slabs of this layer ----------------
-                float4 cur[4], nxt[4];
-                if (l == 0) load_slab0(0, cur);
-                for (int s = 0; s < nslab; ++s, ++it) {
-                    const uint32_t st = it & 1, ph = (it >> 1) & 1;
-                    if (l == 0) {
-                        if (s + 1 < nslab) load_slab0(s + 1, nxt);   // one slab of lookahead
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            cur[q] = *reinterpret_cast<const float4 *>(act + (size_t)(4 * s + q) * (TC_ROWS * 4) + r * 4);
-                    }
-                    mbar_wait(&empty[st], ph ^ 1);
-                    store_slab(st, cur);
-                    fence_proxy_async_smem();
-                    tcgen05_fence_before();
-                    mbar_arrive(&full_a[st]);
-                    if (l == 0) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
-                    }
-                }
-                // ---------------- epilogue of this layer ----------------
-                mbar_wait(&d_ready, dl & 1);
+            for (int l = 1; l < a.nlayers; ++l) {
+                const int nslab = a.kpad[l] / TC_KC;          // == NPAD(l-1) / 32
+                const uint32_t tsrc = tmem_base + (uint32_t)(((l - 1) & 1) * a.region_cols) + lane_addr;
+                const float *bz = bias_s + bias_off;
+                int s = (int)((g - base) & (TC_GROUPS - 1));
+                warp_wait(&d_ready, dl & 1);
                 ++dl;
                 tcgen05_fence_after();
-                const bool last = l == a.nlayers - 1;
-                const bool relu = !last || a.relu_last;
-                const int npad = NPAD(l);
-                const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
-                for (int c0 = 0; c0 < npad; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld_32x16(trow + (uint32_t)c0, v);
+                TC_STAMP(10 + l);
+                uint32_t v[32];
+                if (s < nslab) tmem_ld_32x32(tsrc + (uint32_t)(TC_KC * s), v);
+                for (; s < nslab; s += TC_GROUPS) {
                     tmem_ld_wait();
+                    float4 x0[4], x1[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b4 = *reinterpret_cast<const float4 *>(bz + s * TC_KC + 4 * q);
+                        x0[q].x = fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, 0.f);
+                        x0[q].y = fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.f);
+                        x0[q].z = fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.f);
+                        x0[q].w = fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.f);
+                        const float4 c4 = *reinterpret_cast<const float4 *>(bz + s * TC_KC + 16 + 4 * q);
+                        x1[q].x = fmaxf(__uint_as_float(v[16 + 4 * q + 0]) + c4.x, 0.f);
+                        x1[q].y = fmaxf(__uint_as_float(v[16 + 4 * q + 1]) + c4.y, 0.f);
+                        x1[q].z = fmaxf(__uint_as_float(v[16 + 4 * q + 2]) + c4.z, 0.f);
+                        x1[q].w = fmaxf(__uint_as_float(v[16 + 4 * q + 3]) + c4.w, 0.f);
+                    }
+                    if (s + TC_GROUPS < nslab) tmem_ld_32x32(tsrc + (uint32_t)(TC_KC * (s + TC_GROUPS)), v);   // overlap the next TMEM read
+                    acquire(base + s);
+                    store_half(base + s, 0, x0);
+                    store_half(base + s, 1, x1);
+                    release(base + s);
+                }
+                base += nslab;
+                bias_off += NPAD(l - 1);
+                TC_STAMP(20 + l);
+            }
+            // ---------------- last epilogue: the groups alternate 16-column chunks ----------------
+            {
+                const int l = a.nlayers - 1;
+                const int npad = NPAD(l);
+                const uint32_t tsrc = tmem_base + (uint32_t)((l & 1) * a.region_cols) + lane_addr;
+                warp_wait(&d_ready, dl & 1);
+                ++dl;
+                tcgen05_fence_after();
+                TC_STAMP(30);
+                uint32_t v[16];
+                int c0 = 16 * g;
+                if (c0 < npad) tmem_ld_32x16(tsrc + (uint32_t)c0, v);
+                for (; c0 < npad; c0 += 16 * TC_GROUPS) {
+                    tmem_ld_wait();
+                    if (a.dbg & 8) break;
                     float x[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float t = __uint_as_float(v[j]) + bias_s[bias_off + c0 + j];
-                        x[j] = relu ? fmaxf(t, 0.f) : t;
+                        x[j] = a.relu_last ? fmaxf(t, 0.f) : t;
                     }
-                    if (!last) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4 *>(act + (size_t)(c0 / 4 + q) * (TC_ROWS * 4) + r * 4) =
-                                make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-                    } else if (a.group > 0) {
+                    if (c0 + 16 * TC_GROUPS < npad) tmem_ld_32x16(tsrc + (uint32_t)(c0 + 16 * TC_GROUPS), v);
+                    if (a.group > 0) {
                         // max over the 32 rows of this warp, column by column; lane j keeps column c0+j
                         uint32_t keep = 0;
 #pragma unroll
@@ -352,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
                             const uint32_t m = __reduce_max_sync(kFull, valid ? __float_as_uint(x[j]) : 0u);
                             if (lane == j) keep = m;
                         }
-                        if (lane < 16) red[warp * 256 + c0 + lane] = __uint_as_float(keep);
+                        if (lane < 16) red[(warp & 3) * 256 + c0 + lane] = __uint_as_float(keep);
                     } else if (valid) {
                         float *dst = a.out + grow * a.ldo + col_off + c0;
                         if (c0 + 16 <= cout_last && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -366,50 +476,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(TcArgs a) {
                         }
                     }
                 }
-                if (last && a.group > 0) {
-                    // combine the per-warp maxima of the warps that share a centroid and write it out
-                    const int wpg = a.group / 32;                 // warps per centroid: 1, 2 or 4
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (a.group > 0) {
+                    // combine the per-warp maxima of the warps that share a group and write them out
+                    const int wpg = a.group / 32;                 // row-warps per group: 1, 2 or 4
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                     const int ngroups = 4 / wpg;
-                    for (int o = tid; o < ngroups * npad; o += 128) {
-                        const int g = o / npad, c = o - g * npad;
-                        const int64_t cen = (tile * TC_ROWS) / a.group + g;
+                    for (int o = tid; o < ngroups * npad; o += TC_PROD) {
+                        const int gi = o / npad, c = o - gi * npad;
+                        const int64_t cen = (tile * TC_ROWS) / a.group + gi;
                         if (c >= cout_last || cen * a.group >= a.rows) continue;
-                        float m = red[(g * wpg) * 256 + c];
-                        for (int w = 1; w < wpg; ++w) m = fmaxf(m, red[(g * wpg + w) * 256 + c]);
+                        float m = red[(gi * wpg) * 256 + c];
+                        for (int w = 1; w < wpg; ++w) m = fmaxf(m, red[(gi * wpg + w) * 256 + c]);
                         a.out[cen * a.ldo + col_off + c] = m;
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");   // red aliases a_stage[0]
                 }
                 tcgen05_fence_before();
-                bias_off += npad;
+                TC_STAMP(31);
             }
         }
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<TC_TMEM_COLS>(tmem_d);
+    if (warp == TC_PROD / 32) tmem_dealloc_dyn(tmem_base, (uint32_t)a.tmem_cols);
 }
 
-// weights -> [slab][plane hi|lo][chunk][npad][4], pre-split, zero padded; bias -> [npad]
+// weights -> [slab][plane hi|lo][8 chunks][npad][4], pre-split, zero padded; bias -> [npad]
 __global__ void pack_tc_kernel(int cin, int cout, int kpad, int npad, const float *__restrict__ w,
                                const float *__restrict__ bias, float *__restrict__ wpk, float *__restrict__ bp) {
     const int nslab = kpad / TC_KC;
-    const int per_slab = 2 * 4 * npad * 4;
-    const int total = nslab * per_slab / 2;  // one thread per (slab, chunk, n, e) -> writes hi and lo
+    const int plane = TC_NCHUNK * npad * 4;          // floats per plane
+    const int total = nslab * plane;                 // one thread per (slab, chunk, n, e) -> writes hi and lo
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int e = i & 3;
         const int n = (i >> 2) % npad;
-        const int q = ((i >> 2) / npad) & 3;
-        const int s = (i >> 2) / npad / 4;
+        const int q = ((i >> 2) / npad) % TC_NCHUNK;
+        const int s = (i >> 2) / npad / TC_NCHUNK;
         const int k = s * TC_KC + q * 4 + e;
         const float v = (k < cin && n < cout) ? w[(size_t)n * cin + k] : 0.f;
-        uint32_t h;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-        const float hi = __uint_as_float(h);
-        const size_t o = (size_t)s * per_slab + ((size_t)q * npad + n) * 4 + e;
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        const size_t o = (size_t)s * 2 * plane + ((size_t)q * npad + n) * 4 + e;
         wpk[o] = hi;
-        wpk[o + (size_t)4 * npad * 4] = v - hi;
+        wpk[o + plane] = lo;
     }
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < npad; c += gridDim.x * blockDim.x)
         bp[c] = (c < cout && bias) ? bias[c] : 0.f;
@@ -418,21 +527,29 @@ __global__ void pack_tc_kernel(int cin, int cout, int kpad, int npad, const floa
 struct TcLayout {
     int nlayers, kpad[CAPTRA_MAX_MLP_LAYERS], npad[CAPTRA_MAX_MLP_LAYERS];
     size_t off_w[CAPTRA_MAX_MLP_LAYERS], off_b[CAPTRA_MAX_MLP_LAYERS], total_floats;
-    int wstage_bytes, act_bytes, bias_floats, nsplit, last_npad;
+    int wstage_bytes, bias_floats, nsplit, last_npad;
+    int nstages, region_cols, tmem_cols, target_occ;
     size_t smem_bytes;
     bool supported;
 };
+
+static int pow2_at_least(int v, int lo) {
+    int p = lo;
+    while (p < v) p <<= 1;
+    return p;
+}
 
 static TcLayout tc_layout(const captra_mlp_desc &d) {
     TcLayout L{};
     L.nlayers = d.nlayers;
     L.supported = true;
-    size_t off = 0;
-    int cin = d.cin, npmax = 16, actmax = 0;
     L.nsplit = 1;
+    size_t off = 0;
+    int cin = d.cin, npmax = 32;
     for (int l = 0; l < d.nlayers; ++l) {
         L.kpad[l] = round_up(cin, TC_KC);
-        L.npad[l] = round_up(d.cout[l], 16);
+        // a non-last layer's accumulator columns are the next layer's K: pad to whole slabs
+        L.npad[l] = round_up(d.cout[l], l < d.nlayers - 1 ? TC_KC : 16);
         if (L.npad[l] > 256) {
             if (d.nlayers == 1) {   // one wide layer: 256-column chunks over grid.y
                 L.nsplit = ceil_div(L.npad[l], 256);
@@ -442,16 +559,22 @@ static TcLayout tc_layout(const captra_mlp_desc &d) {
             }
         }
         npmax = max(npmax, min(L.npad[l], 256));
-        if (l < d.nlayers - 1) actmax = max(actmax, L.npad[l]);
         L.off_w[l] = off; off += (size_t)L.kpad[l] * L.npad[l] * 2;
         L.off_b[l] = off; off += L.npad[l];
         L.bias_floats += L.npad[l];
-        cin = d.cout[l];
+        cin = L.npad[l];           // the next layer sees the padded width (zero weights on the pad)
     }
     L.total_floats = off;
-    L.wstage_bytes = 2 * 4 * npmax * 16;
-    L.act_bytes = (actmax / 4) * TC_CHUNK_BYTES;
-    L.smem_bytes = (size_t)2 * TC_A_STAGE + 2 * (size_t)L.wstage_bytes + L.act_bytes + (size_t)L.bias_floats * 4 + 4 * 256 * 4;
+    L.wstage_bytes = 2 * TC_NCHUNK * npmax * 16;
+    // TMEM: accumulators of consecutive layers ping-pong between two regions
+    L.region_cols = pow2_at_least(npmax, 32);
+    L.tmem_cols = d.nlayers > 1 ? 2 * L.region_cols : L.region_cols;
+    L.target_occ = 1;
+    // 4 pipeline stages if they fit in 227 KB, else 2
+    const size_t fixed = (size_t)L.bias_floats * 4 + 256;
+    const size_t per_stage = (size_t)TC_A_STAGE + L.wstage_bytes;
+    L.nstages = (fixed + 4 * per_stage <= 225 * 1024) ? 4 : 2;
+    L.smem_bytes = fixed + (size_t)L.nstages * per_stage;
     if (L.smem_bytes > 225 * 1024) L.supported = false;
     return L;
 }
@@ -466,7 +589,7 @@ bool tc_supported(const captra_mlp_desc *d) { return tc_layout(*d).supported; }
 int tc_pack(const captra_mlp_desc *d, void *packed, cudaStream_t stream) {
     const TcLayout L = tc_layout(*d);
     CAPTRA_REQUIRE(L.supported, "mlp_pack(tc): layer widths not supported by the tcgen05 path");
-    int cin = d->cin;
+    int cin = d->cin;      // true input width of layer l (the packed K is zero padded to L.kpad[l])
     for (int l = 0; l < d->nlayers; ++l) {
         float *base = reinterpret_cast<float *>(packed);
         for (int y = 0; y < L.nsplit; ++y) {   // nsplit > 1 only for a single wide layer
@@ -492,8 +615,10 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, size
         a.wpk[l] = reinterpret_cast<const float *>(packed) + L.off_w[l];
         a.bias[l] = reinterpret_cast<const float *>(packed) + L.off_b[l];
     }
-    a.wstage_bytes = L.wstage_bytes; a.act_bytes = L.act_bytes; a.bias_floats = L.bias_floats;
+    a.wstage_bytes = L.wstage_bytes; a.bias_floats = L.bias_floats;
+    a.region_cols = L.region_cols; a.tmem_cols = L.tmem_cols; a.nst_log2 = L.nstages == 4 ? 2 : 1;
     a.nsplit = L.nsplit; a.last_npad = L.last_npad; a.cout_total = d->cout[d->nlayers - 1];
+    { const char *e = getenv("CAPTRA_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
     *smem = L.smem_bytes;
     return CAPTRA_OK;
 }
@@ -501,10 +626,14 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, size
 template <int MODE>
 static int tc_launch(TcArgs &a, size_t smem, cudaStream_t stream) {
     auto kern = mlp_tc_kernel<MODE>;
-    CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+    CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
-    const int nsm = max(1, sm_count() / a.nsplit);
-    const int gx = a.ntiles < nsm ? (int)a.ntiles : nsm;
+    int occ = 1;
+    CAPTRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TC_THREADS, smem));
+    occ = max(1, min(occ, 512 / a.tmem_cols));      // co-resident CTAs also share the 512 TMEM columns
+    const int64_t slots = (int64_t)max(1, sm_count() / a.nsplit) * occ;
+    const int gx = (int)(a.ntiles < slots ? a.ntiles : slots);
     kern<<<dim3(gx, a.nsplit), TC_THREADS, smem, stream>>>(a);
     CAPTRA_CHECK_LAUNCH("mlp_tc");
     return CAPTRA_OK;
@@ -543,6 +672,17 @@ int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const flo
 }  // namespace captra
 
 using namespace captra;
+
+extern "C" int captra_debug_tc_timestamps(long long *out_host, int max_pairs) {
+    int n = 0;
+    CAPTRA_CUDA(cudaDeviceSynchronize());
+    CAPTRA_CUDA(cudaMemcpyFromSymbol(&n, g_tc_ts_n, sizeof(int)));
+    if (n > max_pairs) n = max_pairs;
+    CAPTRA_CUDA(cudaMemcpyFromSymbol(out_host, g_tc_ts, sizeof(long long) * 2 * n));
+    int zero = 0;
+    CAPTRA_CUDA(cudaMemcpyToSymbol(g_tc_ts_n, &zero, sizeof(int)));
+    return n;
+}
 
 extern "C" int captra_debug_umma_gemm(int k, int n, const float *A, const float *W, float *D, int terms,
                                       captra_stream_t stream) {

@@ -131,14 +131,18 @@ __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// fp32 -> (hi, lo) with hi = round-to-nearest TF32 (low 13 mantissa bits zero) and lo = x - hi
-// exactly; hi*hi' + lo*hi' + hi*lo' then carries ~21 mantissa bits ("3xTF32").
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+// fp32 -> (hi, lo): hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of (x - hi).
+// hi*hi' + lo*hi' + hi*lo' then carries ~21 mantissa bits ("3xTF32").  lo is rounded here because
+// the tensor core TRUNCATES the 13 low mantissa bits of its fp32 inputs: a truncated lo would be
+// biased toward zero and the bias adds up linearly over K instead of as sqrt(K).
+__device__ __forceinline__ float tf32_rna(float x) {
     uint32_t h;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    lo = x - hi;
-    if (!(fabsf(hi) <= 3.0e38f)) lo = 0.f;  // inf/NaN: do not manufacture inf - inf
+    return __uint_as_float(h);
+}
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - hi);   // x = +-inf gives lo = NaN: an overflowed activation poisons the row, as in fp32 BN/ReLU chains it soon would
 }
 
 }  // namespace tc
