@@ -18,6 +18,9 @@ int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const
 int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
                  int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
                  int group, cudaStream_t stream);
+int tc_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale, const float *in_shift,
+                        int rows_per_cloud, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
+                        int col_off, cudaStream_t stream);
 }  // namespace captra
 
 using namespace captra;
@@ -81,4 +84,18 @@ extern "C" int captra_point_mlp(int64_t rows, const float *segA, int64_t ldA, in
         return tc_point_mlp(rows, segA, ldA, ca, segB, ldB, cb, bcast_rows, d, packed, y, ldy, col_off, group, as_stream(stream));
     set_error("point_mlp: impl %d not available", impl);
     return CAPTRA_ERR_UNSUPPORTED;
+}
+
+extern "C" int captra_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale,
+                                       const float *in_shift, int rows_per_cloud, const captra_mlp_desc *d,
+                                       const void *packed, float *y, int64_t ldy, int col_off, int impl,
+                                       captra_stream_t stream) {
+    int rc = check_desc(d, "point_mlp_affine");
+    if (rc) return rc;
+    CAPTRA_REQUIRE(rows >= 0 && cin >= 1 && rows_per_cloud >= 1, "point_mlp_affine: bad sizes");
+    CAPTRA_REQUIRE(d->cin == cin, "point_mlp_affine: mlp cin=%d but input has %d channels", d->cin, cin);
+    CAPTRA_REQUIRE(impl == 1, "point_mlp_affine: only the tcgen05 path (impl 1) implements normalise-on-load");
+    if (rows == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(x && in_scale && in_shift && packed && y, "point_mlp_affine: null pointer");
+    return tc_point_mlp_affine(rows, x, ldx, cin, in_scale, in_shift, rows_per_cloud, d, packed, y, ldy, col_off, as_stream(stream));
 }

@@ -137,6 +137,7 @@ struct TcArgs {
     float *out; int64_t ldo; int col_off;
     int n, s, cfeat; const float *xyz, *new_xyz, *feats; const int *idx;
     const float *segA; int64_t ldA; int ca; const float *segB; int64_t ldB; int cb; int bcast;
+    const float *in_scale, *in_shift; int rows_per_cloud;   // dense: x <- relu(x * scale[cloud] + shift[cloud]) on load (GroupNorm + ReLU of the producer layer)
     int wstage_bytes, bias_floats, region_cols, tmem_cols, nst_log2;
     int nsplit, last_npad, cout_total;          // single wide layer split into 256-column chunks over grid.y
     int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A stores, 2 no W copies, 4 no MMAs, 8 no last epilogue, 32/128 stamps, 64 no gather
@@ -341,6 +342,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
                     brow = a.segB ? a.segB + (a.bcast ? grow / a.bcast : grow) * a.ldB : nullptr;
                 }
             }
+            const float *nsc = nullptr, *nsh = nullptr;   // per-cloud affine of the input (dense mode)
+            if (MODE == 1 && a.in_scale && valid) {
+                const int64_t cloud = grow / a.rows_per_cloud;
+                nsc = a.in_scale + cloud * a.ca;
+                nsh = a.in_shift + cloud * a.ca;
+            }
             auto in0 = [&](int c) -> float {     // layer-0 input element c of this row
                 if (!valid) return 0.f;
                 if (MODE == 0) {
@@ -369,6 +376,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         v[q] = make_float4(in0(c0 + 4 * q), in0(c0 + 4 * q + 1), in0(c0 + 4 * q + 2), in0(c0 + 4 * q + 3));
+                }
+                if (MODE == 1 && nsc) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float *e = reinterpret_cast<float *>(&v[q]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = c0 + 4 * q + j;
+                            e[j] = c < a.ca ? fmaxf(fmaf(e[j], __ldg(nsc + c), __ldg(nsh + c)), 0.f) : 0.f;
+                        }
+                    }
                 }
             };
             TC_STAMP(1);
@@ -654,9 +672,10 @@ int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const
     return tc_launch<0>(a, smem, stream);
 }
 
-int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
-                 int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
-                 int group, cudaStream_t stream) {
+static int tc_point_mlp_ex(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
+                           int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
+                           int group, cudaStream_t stream, const float *in_scale, const float *in_shift,
+                           int rows_per_cloud) {
     CAPTRA_REQUIRE(group == 0 || ((group == 32 || group == 64 || group == 128) && d->relu_last),
                    "point_mlp(tc): grouped max needs group in {32,64,128} and a final ReLU");
     TcArgs a{};
@@ -666,12 +685,100 @@ int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const flo
     a.rows = rows; a.group = group;
     a.out = y; a.ldo = ldy; a.col_off = col_off;
     a.segA = segA; a.ldA = ldA; a.ca = ca; a.segB = segB; a.ldB = ldB; a.cb = cb; a.bcast = bcast;
+    a.in_scale = in_scale; a.in_shift = in_shift; a.rows_per_cloud = rows_per_cloud;
     return tc_launch<1>(a, smem, stream);
+}
+
+int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
+                 int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
+                 int group, cudaStream_t stream) {
+    return tc_point_mlp_ex(rows, segA, ldA, ca, segB, ldB, cb, bcast, d, packed, y, ldy, col_off, group, stream, nullptr, nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics -> per-(cloud, channel) affine.  y is point-major [clouds*npts, C]; a group is
+// `cpg` adjacent channels over all npts points of one cloud (blocks.py:73 GroupNorm(C/2, C)).
+//   scale[b,c] = gamma[c] * rstd(b,g),  shift[b,c] = beta[c] - mean(b,g) * scale[b,c]
+// so the consumer layer applies GroupNorm + ReLU as relu(y*scale + shift) while loading its input.
+// One CTA per (cloud, 64-channel block): coalesced 256-byte row segments, fp32 partials per thread,
+// fp64 combine.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) group_norm_affine_kernel(int npts, int C, int cpg, const float *__restrict__ y, int64_t ld,
+                                                                const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                float eps, float *__restrict__ scale, float *__restrict__ shift) {
+    __shared__ double s_sum[16][64], s_sq[16][64];
+    const int b = blockIdx.y, cb = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c0 = cb + tx * 4;
+    float sm[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
+    if (c0 < C) {
+        const float *base = y + ((size_t)b * npts) * ld + c0;
+        const bool vec = (c0 + 4 <= C) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ld & 3) == 0);
+        for (int r = ty; r < npts; r += 16) {
+            float v[4];
+            if (vec) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(base + (size_t)r * ld));
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = (c0 + j < C) ? __ldg(base + (size_t)r * ld + j) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sm[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_sum[ty][tx * 4 + j] = sm[j]; s_sq[ty][tx * 4 + j] = sq[j]; }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        double a = 0, q = 0;
+        for (int i = 0; i < 16; ++i) { a += s_sum[i][threadIdx.x]; q += s_sq[i][threadIdx.x]; }
+        s_sum[0][threadIdx.x] = a; s_sq[0][threadIdx.x] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int c = cb + threadIdx.x;
+        if (c < C) {
+            const int g0 = (threadIdx.x / cpg) * cpg;   // 64 % cpg == 0 is checked on the host
+            double a = 0, q = 0;
+            for (int j = 0; j < cpg; ++j) { a += s_sum[0][g0 + j]; q += s_sq[0][g0 + j]; }
+            const double n = (double)npts * cpg;
+            const double mean = a / n;
+            const double var = fmax(q / n - mean * mean, 0.0);
+            const double rstd = 1.0 / sqrt(var + (double)eps);
+            const double sc = (gamma ? (double)gamma[c] : 1.0) * rstd;
+            scale[(size_t)b * C + c] = (float)sc;
+            shift[(size_t)b * C + c] = (float)((beta ? (double)beta[c] : 0.0) - mean * sc);
+        }
+    }
 }
 
 }  // namespace captra
 
 using namespace captra;
+
+extern "C" int captra_group_norm_affine(int clouds, int npts, int c, int channels_per_group, const float *y,
+                                        int64_t ldy, const float *gamma, const float *beta, float eps,
+                                        float *scale, float *shift, captra_stream_t stream) {
+    CAPTRA_REQUIRE(clouds >= 0 && npts >= 1 && c >= 1, "group_norm_affine: bad sizes");
+    CAPTRA_REQUIRE(channels_per_group >= 1 && 64 % channels_per_group == 0 && c % channels_per_group == 0,
+                   "group_norm_affine: channels_per_group must divide 64 and C");
+    if (clouds == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(y && scale && shift, "group_norm_affine: null pointer");
+    CAPTRA_REQUIRE(clouds <= 65535, "group_norm_affine: too many clouds");
+    group_norm_affine_kernel<<<dim3(ceil_div(c, 64), clouds), 256, 0, as_stream(stream)>>>(npts, c, channels_per_group, y, ldy, gamma,
+                                                                                          beta, eps, scale, shift);
+    CAPTRA_CHECK_LAUNCH("group_norm_affine");
+    return CAPTRA_OK;
+}
+
+namespace captra {
+int tc_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale, const float *in_shift,
+                        int rows_per_cloud, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
+                        int col_off, cudaStream_t stream) {
+    return tc_point_mlp_ex(rows, x, ldx, cin, nullptr, 0, 0, 0, d, packed, y, ldy, col_off, 0, stream, in_scale, in_shift, rows_per_cloud);
+}
+}  // namespace captra
 
 extern "C" int captra_debug_tc_timestamps(long long *out_host, int max_pairs) {
     int n = 0;

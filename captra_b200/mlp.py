@@ -152,3 +152,36 @@ class PackedMLP:
                   self._pack(impl).data_ptr(), _lib.ptr(out, f32, "out"), out.shape[-1], col_off, group, impl,
                   _lib.stream_ptr(self.device), device=self.device)
         return out
+
+    def rows_affine(self, x, scale, shift, rows_per_cloud, out=None, col_off=0):
+        """Single-segment pointwise MLP whose input is normalised on load:
+        row r of cloud b = r // rows_per_cloud enters as relu(x[r] * scale[b] + shift[b])
+        (GroupNorm + ReLU of the producer layer, see group_norm_affine).  tcgen05 path only."""
+        f32 = torch.float32
+        if self._pick(1) != 1 or self._layers is not None:
+            raise _lib.CaptraError("rows_affine needs a chain the fused tcgen05 kernel supports")
+        R, cin = x.shape
+        if out is None:
+            out = torch.empty(R, self.cout, dtype=f32, device=self.device)
+        _lib.call("point_mlp[R=%d,C=%d->%s,g=0,impl=1,affine]" % (R, self.cin, "-".join(map(str, self.couts))),
+                  _lib.load().captra_point_mlp_affine, R, _lib.ptr(x, f32, "x"), x.stride(0), cin,
+                  _lib.ptr(scale, f32, "scale"), _lib.ptr(shift, f32, "shift"), rows_per_cloud,
+                  ctypes.byref(self.desc), self._pack(1).data_ptr(), _lib.ptr(out, f32, "out"), out.shape[-1], col_off, 1,
+                  _lib.stream_ptr(self.device), device=self.device)
+        return out
+
+
+def group_norm_affine(y, clouds, npts, gn):
+    """Per-(cloud, channel) scale/shift equivalent to `gn` (torch.nn.GroupNorm) applied to the pre-norm
+    activation y [clouds*npts, C] (point-major): GroupNorm(y) == y * scale + shift."""
+    C = y.shape[1]
+    cpg = C // gn.num_groups
+    scale = torch.empty(clouds, C, dtype=torch.float32, device=y.device)
+    shift = torch.empty_like(scale)
+    g = gn.weight.detach().contiguous() if gn.weight is not None else None
+    b = gn.bias.detach().contiguous() if gn.bias is not None else None
+    _lib.call("group_norm_affine[B=%d,n=%d,C=%d]" % (clouds, npts, C), _lib.load().captra_group_norm_affine,
+              clouds, npts, C, cpg, _lib.ptr(y, torch.float32, "y"), y.stride(0),
+              g.data_ptr() if g is not None else None, b.data_ptr() if b is not None else None, float(gn.eps),
+              scale.data_ptr(), shift.data_ptr(), _lib.stream_ptr(y.device), device=y.device)
+    return scale, shift

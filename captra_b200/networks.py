@@ -14,7 +14,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import mlp as _mlp
 from .backbones import PointNet2Msg
+from .mlp import PackedMLP, fold_conv_bn, group_norm_affine
+from .pointnet_utils import _FusedCache, _needs_autograd
 from .pose_utils.pose_fit import part_fit_st_no_ransac
 
 
@@ -103,6 +106,24 @@ class MLPConv1d(nn.Module):
     def forward(self, x):
         return self.model(x)
 
+    def forward_pm(self, feat_pm):
+        """Fused inference path on point-major features [B,N,C] -> raw head output [B,N,D].
+        Every conv1d is one tcgen05 launch; GroupNorm + ReLU never materialise: the statistics of a
+        layer's pre-norm output become a per-(cloud, channel) affine that the next layer applies
+        while it loads its operand."""
+        B, N, C = feat_pm.shape
+        convs = [m for m in self.model if isinstance(m, nn.Conv1d)]
+        gns = [m for m in self.model if isinstance(m, nn.GroupNorm)]
+        if not hasattr(self, "_cache"):
+            self._cache = _FusedCache()
+        packs = self._cache.get(self, lambda: [PackedMLP([c.weight.detach().reshape(c.out_channels, c.in_channels)],
+                                                         [c.bias.detach()], relu_last=False, impl=1) for c in convs])
+        y = packs[0].rows(feat_pm.reshape(B * N, C))
+        for i in range(1, len(convs)):
+            scale, shift = group_norm_affine(y, B, N, gns[i - 1])
+            y = packs[i].rows_affine(y, scale, shift, N)
+        return y.view(B, N, -1)
+
 
 class RotationRegressor(nn.Module):
     """blocks.py:168-193."""
@@ -140,12 +161,32 @@ class CoordNet(nn.Module):
         self.seg_head = get_point_mlp(in_dim, seg_dim, [], acti='none')
         self.nocs_head = get_point_mlp(in_dim, 3 * self.num_parts, cfg['network']['nocs_head_dims'], acti='sigmoid')
 
+    def _packed_heads(self):
+        def build():
+            seg = PackedMLP([self.seg_head[0].weight.detach().reshape(self.seg_head[0].out_channels, -1)],
+                            [self.seg_head[0].bias.detach()], relu_last=False)
+            convs = [m for m in self.nocs_head if isinstance(m, nn.Conv1d)]
+            bns = [m for m in self.nocs_head if isinstance(m, nn.BatchNorm1d)]
+            wb = [fold_conv_bn(c, bns[i] if i < len(bns) else None) for i, c in enumerate(convs)]
+            nocs = PackedMLP([w for w, _ in wb], [b for _, b in wb], relu_last=False)
+            return seg, nocs
+        if not hasattr(self, "_cache"):
+            self._cache = _FusedCache()
+        return self._cache.get(self, build)
+
     def forward(self, input, test=False):
+        assert 'gt_part' not in input, "training-time pose branch (networks.py:54-108) is not mirrored"
         cam = canonicalize(input['points'], input['points_mean'], input['canon_pose'])
+        if not _needs_autograd(self, cam):
+            feat = self.backbone.forward_pm(cam)                    # [B,N,C] point-major
+            B, N, C = feat.shape
+            seg_mlp, nocs_mlp = self._packed_heads()
+            seg = F.softmax(seg_mlp.rows(feat.reshape(B * N, C)).view(B, N, -1), dim=-1).transpose(1, 2)
+            nocs = (torch.sigmoid(nocs_mlp.rows(feat.reshape(B * N, C))) - 0.5).view(B, N, -1).transpose(1, 2)
+            return {'seg': seg, 'nocs': nocs, 'points': cam}
         feat = self.backbone(cam)
         seg = F.softmax(self.seg_head(feat), dim=1)
         nocs = self.nocs_head(feat) - 0.5
-        assert 'gt_part' not in input, "training-time pose branch (networks.py:54-108) is not mirrored"
         return {'seg': seg, 'nocs': nocs, 'points': cam}
 
 
@@ -164,11 +205,20 @@ class RotationRegressionBackbone(nn.Module):
         copy p, masked mean over part p's points (networks.py:127-139 restricted to the diagonal
         that networks.py:200-203 keeps)."""
         P = self.num_parts
-        feat = self.encoder(cam)                                   # [B*P, C, N]
-        feat = feat.reshape(batch_size, P, feat.shape[1], feat.shape[2])
+        fused = _mlp.DEFAULT_IMPL == 1 and not _needs_autograd(self, cam)
+        if fused:
+            feat_pm = self.encoder.forward_pm(cam)                 # [B*P, N, C] point-major
+            feat_pm = feat_pm.reshape(batch_size, P, feat_pm.shape[1], feat_pm.shape[2])
+        else:
+            feat = self.encoder(cam)                               # [B*P, C, N]
+            feat = feat.reshape(batch_size, P, feat.shape[1], feat.shape[2])
         out = []
         for p in range(P):
-            raw = self.pose_pred.post(self.pose_pred.rtvec_head[p](feat[:, p]))   # [B, D, N]
+            if fused:
+                raw = self.pose_pred.rtvec_head[p].forward_pm(feat_pm[:, p].contiguous()).transpose(1, 2)
+            else:
+                raw = self.pose_pred.rtvec_head[p](feat[:, p])
+            raw = self.pose_pred.post(raw)                                          # [B, D, N]
             mask = (labels == p).float().unsqueeze(1)                               # [B, 1, N]
             cnt = mask.sum(-1)
             mean = (raw * mask).sum(-1) / torch.clamp_min(cnt, 1.0)

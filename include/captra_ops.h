@@ -164,6 +164,19 @@ int captra_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const
                      const void *packed, float *y, int64_t ldy, int col_off, int group, int impl,
                      captra_stream_t stream);
 
+/* GroupNorm folded into the consumer layer (RotationRegressor heads, blocks.py:146-193: conv1d ->
+ * GroupNorm(C/2 groups) -> ReLU).  captra_group_norm_affine turns the statistics of a pre-norm
+ * activation y [clouds*npts, C] (point-major) into per-(cloud, channel) scale/shift; the next
+ * layer then reads relu(y * scale[cloud] + shift[cloud]) through captra_point_mlp_affine (tcgen05
+ * path only), so the normalised tensor is never written. */
+int captra_group_norm_affine(int clouds, int npts, int c, int channels_per_group, const float *y,
+                             int64_t ldy, const float *gamma, const float *beta, float eps,
+                             float *scale, float *shift, captra_stream_t stream);
+int captra_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale,
+                            const float *in_shift, int rows_per_cloud, const captra_mlp_desc *mlp,
+                            const void *packed, float *y, int64_t ldy, int col_off, int impl,
+                            captra_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * 4. Pose fit (pose_utils/procrustes.py, pose_utils/pose_fit.py) -- Python in the reference,
  *    with torch.svd on the CPU (procrustes.py:27-30,170-174); here on the device.
@@ -196,10 +209,12 @@ int captra_part_fit_st(int b, int p, int n, const int64_t *labels, const float *
 
 /* ------------------------------------------------------------------------------------------
  * 5. Unit-test doorway for the tcgen05 primitives: D[128,n] = A[128,k] * W[n,k]^T on one CTA
- *    (terms = 1: single-pass TF32, 3: 3xTF32).  Not used by the product path.
+ *    (terms = 1: single-pass TF32, 3: 3xTF32), and the clock64 phase stamps the fused kernel
+ *    records when CAPTRA_TC_DBG has bit 32/128 set.  Not used by the product path.
  * ---------------------------------------------------------------------------------------- */
 int captra_debug_umma_gemm(int k, int n, const float *A, const float *W, float *D, int terms,
                            captra_stream_t stream);
+int captra_debug_tc_timestamps(long long *out_host, int max_pairs);
 
 #ifdef __cplusplus
 }

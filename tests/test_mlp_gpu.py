@@ -173,3 +173,35 @@ def test_backbone_full_size_shapes(impl, cuda):
         ref = net(pts.clone().requires_grad_(True)).detach()   # unfused torch composition
         assert fused.shape == (4, 128, 4096)
         torch.testing.assert_close(fused, ref, rtol=2e-4, atol=2e-5)
+
+
+def test_rotation_head_groupnorm_fused_vs_torch(cuda):
+    """RotationRegressor head (blocks.py:146-193: conv1d + GroupNorm(C/2) + ReLU x3 + conv1d): the fused
+    path (tcgen05 GEMMs, GroupNorm folded into the consumer's operand load) vs the torch modules."""
+    from captra_b200.networks import MLPConv1d
+    torch.manual_seed(0)
+    head = MLPConv1d(128, [512, 512, 256, 6]).to(cuda).eval()
+    for m in head.modules():
+        if isinstance(m, torch.nn.GroupNorm):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.2)
+    B, N = 3, 4096
+    feat = torch.randn(B, 128, N, device=cuda)
+    with torch.no_grad():
+        want = head(feat)                                            # [B, 6, N]
+        got = head.forward_pm(feat.transpose(1, 2).contiguous()).transpose(1, 2)
+    torch.testing.assert_close(got, want, rtol=1e-3, atol=2e-4)      # 3xTF32 through 4 layers + GroupNorm
+
+
+def test_group_norm_affine_kernel(cuda):
+    from captra_b200.mlp import group_norm_affine
+    torch.manual_seed(1)
+    for (B, N, C) in ((2, 4096, 512), (3, 100, 256), (1, 777, 64)):
+        gn = torch.nn.GroupNorm(C // 2, C).to(cuda)
+        gn.weight.data.uniform_(0.5, 1.5)
+        gn.bias.data.normal_(0, 0.2)
+        y = (torch.randn(B * N, C, device=cuda) * 2 + 0.5)
+        scale, shift = group_norm_affine(y, B, N, gn)
+        got = y.view(B, N, C) * scale.view(B, 1, C) + shift.view(B, 1, C)
+        want = gn(y.view(B, N, C).transpose(1, 2)).transpose(1, 2)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)

@@ -19,6 +19,44 @@ def _cpu(d):
     return {k: v.detach().cpu() for k, v in d.items()}
 
 
+def _make_nocs_meaningful(coordnet, num_parts):
+    """Random weights give NOCS predictions uncorrelated with the cloud, and the scale fit then is a
+    small difference of large sums (condition number ~60): any 1e-5 feature noise shows up as 1e-3 on
+    the scale.  A trained CoordNet predicts NOCS ~ canonical coordinates, so route the canonicalised
+    xyz (skip connection of fp1, backbones.py:67) through to the NOCS head: channel i carries relu(x_i),
+    channel 3+i relu(-x_i), the head outputs sigmoid(4 x_i + 0.05 * (random deep features)) - 0.5."""
+    bb = coordnet.backbone
+    with torch.no_grad():
+        def passthrough(conv, bn, first=False):
+            w = conv.weight
+            w[:6] = 0
+            if first:
+                for i in range(3):
+                    w[i, i] = 1.0
+                    w[3 + i, i] = -1.0
+            else:
+                for i in range(6):
+                    w[i, i] = 1.0
+            conv.bias[:6] = 0
+            if bn is not None:
+                bn.weight[:6] = 1.0
+                bn.bias[:6] = 0
+                bn.running_mean[:6] = 0
+                bn.running_var[:6] = 1.0 - bn.eps
+        passthrough(bb.fp1.mlp_convs[0], bb.fp1.mlp_bns[0], first=True)
+        passthrough(bb.fp1.mlp_convs[1], bb.fp1.mlp_bns[1])
+        passthrough(bb.conv1, bb.bn1)
+        passthrough(coordnet.nocs_head[0], coordnet.nocs_head[1])
+        last = coordnet.nocs_head[3]
+        last.weight.mul_(0.05)
+        last.bias.zero_()
+        for p in range(num_parts):
+            for i in range(3):
+                last.weight[3 * p + i, :6] = 0
+                last.weight[3 * p + i, i] = 4.0
+                last.weight[3 * p + i, 3 + i] = -4.0
+
+
 @pytest.fixture(params=[0, 1])
 def impl(request, monkeypatch):
     from captra_b200 import mlp
@@ -31,7 +69,9 @@ def test_track_step_vs_cpu_restatement(category, B, impl, cuda):
     from captra_b200 import track
     from oracle import frame_ref
     cfg = track.make_cfg(category)
-    trk = track.Tracker(cfg, seed=3).to(cuda).eval()
+    trk = track.Tracker(cfg, seed=3)
+    _make_nocs_meaningful(trk.npcs_net, cfg["num_parts"])
+    trk = trk.to(cuda).eval()
     batch = track.synthetic_track_batch(B, category, n=4096, seed=5)
     pts = torch.from_numpy(batch["points"])
     mean = torch.from_numpy(batch["points_mean"])
