@@ -234,7 +234,7 @@ def main():
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False   # heads are torch fp32; keep them true fp32 like the reference
     torch.backends.cudnn.allow_tf32 = False
-    from captra_b200 import _lib, track
+    from captra_b200 import _lib, shard, track
     _lib.load()
     cfg = track.make_cfg(w["category"], device=str(dev))
     trk = track.Tracker(cfg, seed=0).to(dev).eval()
@@ -249,18 +249,13 @@ def main():
     stream = torch.cuda.current_stream(dev)
 
     def loss_scalars(pose, gt):
-        """pose-error scalars a tracker logs per batch (model.py:511-593 in spirit): sums + count."""
-        t_err = (pose["translation"] - gt["translation"]).norm(dim=-2).sum()
-        s_err = (pose["scale"] - gt["scale"]).abs().sum()
-        r_err = (pose["rotation"] - gt["rotation"]).pow(2).sum()
-        return torch.stack([t_err, s_err, r_err, torch.tensor(float(B * P), device=dev)])
+        """pose-error sums a tracker logs per batch (test.py:87-99 in spirit): sums + count."""
+        return shard.pose_error_scalars(pose, gt)
 
     def step_resident(i):
         r = resident[i % nb]
         pose = trk.step(r["points"], r["mean"], r["pose"])
-        ls = loss_scalars(pose, pinned[i % nb]["gt"])
-        if world > 1:
-            torch.distributed.all_reduce(ls)
+        ls = shard.all_reduce_scalars(loss_scalars(pose, pinned[i % nb]["gt"]))
         return pose, ls
 
     def barrier():
@@ -301,8 +296,7 @@ def main():
         mean = p["mean"].to(dev, non_blocking=True)
         pose = {k: v.to(dev, non_blocking=True) for k, v in p["pose"].items()}
         new = trk.step(pts, mean, pose)
-        if world > 1:
-            torch.distributed.all_reduce(loss_scalars(new, p["gt"]))
+        shard.all_reduce_scalars(loss_scalars(new, p["gt"]))
         for k in out_host:
             out_host[k].copy_(new[k], non_blocking=True)
         stream.synchronize()               # the tracker consumes the pose of frame t before frame t+1
@@ -333,9 +327,10 @@ def main():
         pk = peaks()
         _lib.PROFILE = []
         nprof = 3
-        for i in range(nprof):
+        for i in range(nprof):          # rank 0 only: no collective in here
             flush.zero_()
-            step_resident(i)
+            r = resident[i % nb]
+            trk.step(r["points"], r["mean"], r["pose"])
         torch.cuda.synchronize(dev)
         prof, _lib.PROFILE = _lib.PROFILE, None
         agg = {}
@@ -387,7 +382,7 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
                                             mlp_impl=int(os.environ.get("CAPTRA_MLP_IMPL", "1")),
-                                            heads="torch fp32 (next row, SURVEY 8f-1)", collective="nccl all_reduce of 4 pose-error scalars per step" if world > 1 else "none"),
+                                            heads="fused: tcgen05 GEMMs + GroupNorm folded into the operand load (impl 1); torch modules for impl 0", collective="nccl all_reduce of 4 pose-error scalars per step" if world > 1 else "none"),
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clocks,

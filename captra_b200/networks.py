@@ -3,12 +3,13 @@ RotationRegressionBackbone / RotationRegressor and PartCanonNet with the same co
 arguments (cfg dict), the same forward(dict) contract and the same state-dict keys, so the
 reference's checkpoints load and EvalTrackModel.forward (model.py:386-478) can drive them.
 
-Scope note (SURVEY section 8f rank 1): the backbone and the pose fit are this package's kernels;
-the small per-point heads (seg / NOCS conv1d, RotationRegressor conv1d + GroupNorm) are still
-plain torch modules here, exactly as in the reference -- they are the next row to fuse.  One
-exact saving is already taken: the reference evaluates all P rotation heads on all B*P
-canonicalised clouds and keeps the diagonal (networks.py:200-203); head p is evaluated only on
-part p's copy here, which yields the same tensors.
+Scope note: in eval mode the per-point heads run on this package's
+kernels too -- seg / NOCS heads as BN-folded fused MLPs, the RotationRegressor heads as one tcgen05
+GEMM per conv1d with GroupNorm + ReLU folded into the consumer's operand load
+(captra_group_norm_affine + captra_point_mlp_affine).  With CAPTRA_MLP_IMPL=0, in training mode or
+under autograd the torch modules run, exactly as in the reference.  One exact saving is taken: the
+reference evaluates all P rotation heads on all B*P canonicalised clouds and keeps the diagonal
+(networks.py:200-203); head p is evaluated only on part p's copy here, which yields the same tensors.
 """
 import torch
 import torch.nn as nn
