@@ -121,8 +121,13 @@ __global__ void __launch_bounds__(128) umma_debug_gemm_kernel(int K, int N, cons
 constexpr int TC_GROUPS = 2;                      // producer groups; group g owns every 2nd slab
 constexpr int TC_PROD = 128 * TC_GROUPS;          // producer / epilogue threads (warps 0-7)
 constexpr int TC_THREADS = TC_PROD + 64;          // + MMA warp (8) + TMA warp (9)
-constexpr int TC_KC = 32;                         // channels per slab (8 chunks of 16 bytes, 4 k-steps of 8)
-constexpr int TC_NCHUNK = TC_KC / 4;
+// A slab is always 8 chunks of 16 bytes per row = 4 k-steps; it spans 32 channels as TF32 (impl 1,
+// 3xTF32) or 64 channels as fp16 (impl 2, "fp16x3": the same hi/lo split with 11-bit mantissas, half
+// the operand bytes and K=16 per MMA; weights are pre-scaled by a power of two per layer so their lo
+// parts stay normal, activations saturate at +-65504).
+constexpr int TC_NCHUNK = 8;
+constexpr int TC_BIAS_PAD = 16;                   // bias region = npad + 16 floats; [npad] = 1 / weight scale
+__host__ __device__ constexpr int tc_kc(bool f16) { return f16 ? 64 : 32; }
 constexpr int TC_A_PLANE = TC_NCHUNK * TC_CHUNK_BYTES;   // bytes of one (hi or lo) A slab plane: 16 KB
 constexpr int TC_A_STAGE = 2 * TC_A_PLANE;        // hi + lo
 constexpr int TC_MAX_STAGES = 4;
@@ -140,6 +145,8 @@ struct TcArgs {
     const float *in_scale, *in_shift; int rows_per_cloud;   // dense: x <- relu(x * scale[cloud] + shift[cloud]) on load (GroupNorm + ReLU of the producer layer)
     int wstage_bytes, bias_floats, region_cols, tmem_cols, nst_log2;
     int nsplit, last_npad, cout_total;          // single wide layer split into 256-column chunks over grid.y
+    int f16;
+    int cin0, klast0;                           // true layer-0 width; k-steps that carry data in layer 0's last slab
     int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A stores, 2 no W copies, 4 no MMAs, 8 no last epilogue, 32/128 stamps, 64 no gather
 };
 
@@ -150,6 +157,52 @@ __device__ __forceinline__ void tmem_alloc_dyn(uint32_t *smem_result, uint32_t n
 __device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// x -> (hi, lo) as fp16 with saturation; returns hi | lo<<16 is NOT what we want: planes are separate
+__device__ __forceinline__ void split_f16(float x, unsigned short &hi, unsigned short &lo) {
+    unsigned short h, l;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    float hf;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
+    hi = h; lo = l;
+}
+// Max over the 32 lanes of a warp for 16 values per lane in 16 shuffles (recursive halving): after
+// the four halving rounds lane l holds column ((l&1)<<3 | (l&2)<<1 | (l&4)>>1 | (l&8)>>3); a final
+// xor-16 round merges the two half-warps.  (redux.sync on the bit patterns is one instruction per
+// value but serialises at ~60 cycles each through the uniform datapath.)
+__device__ __forceinline__ float warp_colmax16(const float (&x)[16], int lane, int &col) {
+    float y[8], z[4], w[2];
+    const bool b0 = lane & 1, b1 = lane & 2, b2 = lane & 4, b3 = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float keep = b0 ? x[j + 8] : x[j], send = b0 ? x[j] : x[j + 8];
+        y[j] = fmaxf(keep, __shfl_xor_sync(kFull, send, 1));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float keep = b1 ? y[j + 4] : y[j], send = b1 ? y[j] : y[j + 4];
+        z[j] = fmaxf(keep, __shfl_xor_sync(kFull, send, 2));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float keep = b2 ? z[j + 2] : z[j], send = b2 ? z[j] : z[j + 2];
+        w[j] = fmaxf(keep, __shfl_xor_sync(kFull, send, 4));
+    }
+    const float keep = b3 ? w[1] : w[0], send = b3 ? w[0] : w[1];
+    float v = fmaxf(keep, __shfl_xor_sync(kFull, send, 8));
+    v = fmaxf(v, __shfl_xor_sync(kFull, v, 16));
+    col = (b0 ? 8 : 0) | (b1 ? 4 : 0) | (b2 ? 2 : 0) | (b3 ? 1 : 0);
+    return v;
+}
+__device__ __forceinline__ uint32_t pack2(unsigned short a, unsigned short b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
 // timing probe: producer thread 0 of CTA 0 stamps clock64() at phase boundaries of its first tiles
 __device__ long long g_tc_ts[512];
@@ -175,8 +228,10 @@ __device__ int g_tc_ts_n;
 // per barrier round), ONE `full` barrier per stage shared by the A producers and the weight TMA
 // (4 warp arrivals + 1 arrive.expect_tx), descriptors advanced by adding to their low word, and
 // two producer groups that alternate slabs so their per-slab latency chains overlap.
-template <int MODE>  // 0: SA gather loader, 1: dense-row loader; the last epilogue is chosen by a.group
+template <int MODE, bool F16>  // MODE 0: SA gather loader, 1: dense-row loader; the last epilogue is chosen by a.group
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
+    constexpr int TC_KC = tc_kc(F16);
+    constexpr int PIECES = TC_KC / 16;             // 16-channel pieces per slab
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], d_ready;
     __shared__ uint32_t tmem_base_s;
@@ -195,8 +250,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
     if (a.nsplit > 1) {
         const int y = blockIdx.y;
         npad_y = (y < a.nsplit - 1) ? 256 : a.last_npad;
-        wpk0 += (size_t)y * a.kpad[0] * 256 * 2;
-        bias0 += y * 256;
+        wpk0 += (size_t)y * (a.kpad[0] / TC_KC) * 2 * TC_NCHUNK * 256 * 4;
+        bias0 += y * (256 + TC_BIAS_PAD);
         col_off += y * 256;
         cout_last = min(256, a.cout_total - y * 256);
     }
@@ -213,8 +268,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
     {   // biases of all layers -> smem
         int off = 0;
         for (int l = 0; l < a.nlayers; ++l) {
-            for (int i = tid; i < NPAD(l); i += TC_THREADS) bias_s[off + i] = __ldg(BIAS(l) + i);
-            off += NPAD(l);
+            for (int i = tid; i < NPAD(l) + TC_BIAS_PAD; i += TC_THREADS) bias_s[off + i] = __ldg(BIAS(l) + i);
+            off += NPAD(l) + TC_BIAS_PAD;
         }
     }
     tcgen05_fence_before();
@@ -230,7 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
             for (int l = 0; l < a.nlayers; ++l) {
                 const int nslab = a.kpad[l] / TC_KC;
                 const uint32_t npad = (uint32_t)NPAD(l);
-                const uint32_t idesc = make_idesc(2, TC_ROWS, (int)npad);
+                const uint32_t idesc = make_idesc(F16 ? 0 : 2, TC_ROWS, (int)npad);
                 const uint32_t b_lbo = npad * 16;
                 const uint64_t b_desc0 = smem_desc_kmajor_noswz(smem_u32(w_stage), b_lbo, 128);
                 const uint32_t b_lo_off = (TC_NCHUNK * b_lbo) >> 4, b_step = (2 * b_lbo) >> 4;   // in 16-byte units
@@ -246,12 +301,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
                     uint64_t al = ah + (TC_A_PLANE >> 4);
                     uint64_t bh = b_desc0 + (uint64_t)((st * (uint32_t)a.wstage_bytes) >> 4);
                     uint64_t bl = bh + b_lo_off;
+                    const int nks = (l == 0 && s == nslab - 1) ? a.klast0 : TC_NCHUNK / 2;   // zero padding needs no MMAs
 #pragma unroll
-                    for (int j = 0; j < TC_KC / 8; ++j) {
-                        if (a.dbg & 4) break;
-                        umma_tf32(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
-                        umma_tf32(tmem_d, ah, bl, idesc, 1u);
-                        umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                    for (int j = 0; j < TC_NCHUNK / 2; ++j) {
+                        if ((a.dbg & 4) || j >= nks) break;
+                        if (F16) {
+                            umma_f16(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
+                            umma_f16(tmem_d, ah, bl, idesc, 1u);
+                            umma_f16(tmem_d, ah, bh, idesc, 1u);
+                        } else {
+                            umma_tf32(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
+                            umma_tf32(tmem_d, ah, bl, idesc, 1u);
+                            umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                        }
                         ah += (2 * TC_CHUNK_BYTES) >> 4; al += (2 * TC_CHUNK_BYTES) >> 4;
                         bh += b_step; bl += b_step;
                     }
@@ -293,19 +355,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
             if (lane == 0) mbar_wait(bar, parity);
             __syncwarp();
         };
-        // store 16 channels (half a slab: chunks 4*half .. 4*half+3) of global slab `it` as hi/lo planes
-        auto store_half = [&](uint32_t it, int half, const float4 (&v)[4]) {
+        // store 16 channels (piece `pc` of the slab) of global slab `it` as hi/lo operand planes
+        auto store16 = [&](uint32_t it, int pc, const float4 (&v)[4]) {
+            if (a.dbg & 1) return;
             const uint32_t st = it & (NST - 1);
-            float *hi = reinterpret_cast<float *>(a_stage + st * TC_A_STAGE) + (4 * half) * (TC_ROWS * 4) + r * 4;
-            float *lo = hi + TC_A_PLANE / 4;
+            float *plane_hi = reinterpret_cast<float *>(a_stage + st * TC_A_STAGE) + r * 4;
+            float *plane_lo = plane_hi + TC_A_PLANE / 4;
+            if (F16) {        // 2 chunks of 8 halfs
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (a.dbg & 1) break;
-                float4 hh, ll;
-                split_tf32(v[q].x, hh.x, ll.x); split_tf32(v[q].y, hh.y, ll.y);
-                split_tf32(v[q].z, hh.z, ll.z); split_tf32(v[q].w, hh.w, ll.w);
-                *reinterpret_cast<float4 *>(hi + q * (TC_ROWS * 4)) = hh;
-                *reinterpret_cast<float4 *>(lo + q * (TC_ROWS * 4)) = ll;
+                for (int q = 0; q < 2; ++q) {
+                    const float e[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
+                    unsigned short hh[8], ll[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) split_f16(e[j], hh[j], ll[j]);
+                    const int chunk = 2 * pc + q;
+                    *reinterpret_cast<uint4 *>(plane_hi + chunk * (TC_ROWS * 4)) =
+                        make_uint4(pack2(hh[0], hh[1]), pack2(hh[2], hh[3]), pack2(hh[4], hh[5]), pack2(hh[6], hh[7]));
+                    *reinterpret_cast<uint4 *>(plane_lo + chunk * (TC_ROWS * 4)) =
+                        make_uint4(pack2(ll[0], ll[1]), pack2(ll[2], ll[3]), pack2(ll[4], ll[5]), pack2(ll[6], ll[7]));
+                }
+            } else {          // 4 chunks of 4 floats
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 hh, ll;
+                    split_tf32(v[q].x, hh.x, ll.x); split_tf32(v[q].y, hh.y, ll.y);
+                    split_tf32(v[q].z, hh.z, ll.z); split_tf32(v[q].w, hh.w, ll.w);
+                    const int chunk = 4 * pc + q;
+                    *reinterpret_cast<float4 *>(plane_hi + chunk * (TC_ROWS * 4)) = hh;
+                    *reinterpret_cast<float4 *>(plane_lo + chunk * (TC_ROWS * 4)) = ll;
+                }
             }
         };
         auto acquire = [&](uint32_t it) {     // wait until the MMAs that last read this slab's stage are done
@@ -364,6 +442,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
             const float *vbase = MODE == 0 ? frow : arow;
             const bool vec_row = valid && vbase && ((reinterpret_cast<uintptr_t>(vbase) & 15) == 0);
             auto load16 = [&](int c0, float4 (&v)[4]) {             // 16 consecutive layer-0 channels
+                if (c0 >= a.cin0) {   // pure padding
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    return;
+                }
                 if (a.dbg & 64) {   // probe: no global gather
 #pragma unroll
                     for (int q = 0; q < 4; ++q) v[q] = make_float4(px, py, pz, 1.f);
@@ -390,23 +473,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
                 }
             };
             TC_STAMP(1);
-            // ---------------- layer 0: this group's slabs, the next one prefetched ----------------
+            // ---------------- layer 0: this group's slabs; each piece's registers are refilled with the
+            // same piece of the group's NEXT slab right after it is stored (one-slab-ahead prefetch) ----
             {
                 const int nslab = a.kpad[0] / TC_KC;
                 int s = (int)((g - base) & (TC_GROUPS - 1));      // first slab of this layer owned by group g
-                float4 c0v[4], c1v[4], n0v[4], n1v[4];
-                if (s < nslab) { load16(s * TC_KC, c0v); load16(s * TC_KC + 16, c1v); }
+                float4 cur[PIECES][4];
+                if (s < nslab) {
+#pragma unroll
+                    for (int pc = 0; pc < PIECES; ++pc) load16(s * TC_KC + 16 * pc, cur[pc]);
+                }
                 for (; s < nslab; s += TC_GROUPS) {
                     const bool more = s + TC_GROUPS < nslab;
-                    if (more) { load16((s + TC_GROUPS) * TC_KC, n0v); load16((s + TC_GROUPS) * TC_KC + 16, n1v); }
                     acquire(base + s);
-                    store_half(base + s, 0, c0v);
-                    store_half(base + s, 1, c1v);
-                    release(base + s);
-                    if (more) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) { c0v[q] = n0v[q]; c1v[q] = n1v[q]; }
+                    for (int pc = 0; pc < PIECES; ++pc) {
+                        store16(base + s, pc, cur[pc]);
+                        if (more) load16((s + TC_GROUPS) * TC_KC + 16 * pc, cur[pc]);
                     }
+                    release(base + s);
                 }
                 base += nslab;
             }
@@ -414,40 +499,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
             // ---------------- layers 1..L-1: previous accumulator -> next operand ----------------
             int bias_off = 0;
             for (int l = 1; l < a.nlayers; ++l) {
-                const int nslab = a.kpad[l] / TC_KC;          // == NPAD(l-1) / 32
+                const int nslab = a.kpad[l] / TC_KC;          // == NPAD(l-1) / TC_KC
                 const uint32_t tsrc = tmem_base + (uint32_t)(((l - 1) & 1) * a.region_cols) + lane_addr;
                 const float *bz = bias_s + bias_off;
+                const float inv = bz[NPAD(l - 1)];            // 1 / weight scale of layer l-1
                 int s = (int)((g - base) & (TC_GROUPS - 1));
                 warp_wait(&d_ready, dl & 1);
                 ++dl;
                 tcgen05_fence_after();
                 TC_STAMP(10 + l);
-                uint32_t v[32];
-                if (s < nslab) tmem_ld_32x32(tsrc + (uint32_t)(TC_KC * s), v);
+                uint32_t v[16];
+                if (s < nslab) tmem_ld_32x16(tsrc + (uint32_t)(TC_KC * s), v);
                 for (; s < nslab; s += TC_GROUPS) {
-                    tmem_ld_wait();
-                    float4 x0[4], x1[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 b4 = *reinterpret_cast<const float4 *>(bz + s * TC_KC + 4 * q);
-                        x0[q].x = fmaxf(__uint_as_float(v[4 * q + 0]) + b4.x, 0.f);
-                        x0[q].y = fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.f);
-                        x0[q].z = fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.f);
-                        x0[q].w = fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.f);
-                        const float4 c4 = *reinterpret_cast<const float4 *>(bz + s * TC_KC + 16 + 4 * q);
-                        x1[q].x = fmaxf(__uint_as_float(v[16 + 4 * q + 0]) + c4.x, 0.f);
-                        x1[q].y = fmaxf(__uint_as_float(v[16 + 4 * q + 1]) + c4.y, 0.f);
-                        x1[q].z = fmaxf(__uint_as_float(v[16 + 4 * q + 2]) + c4.z, 0.f);
-                        x1[q].w = fmaxf(__uint_as_float(v[16 + 4 * q + 3]) + c4.w, 0.f);
-                    }
-                    if (s + TC_GROUPS < nslab) tmem_ld_32x32(tsrc + (uint32_t)(TC_KC * (s + TC_GROUPS)), v);   // overlap the next TMEM read
                     acquire(base + s);
-                    store_half(base + s, 0, x0);
-                    store_half(base + s, 1, x1);
+#pragma unroll
+                    for (int pc = 0; pc < PIECES; ++pc) {
+                        tmem_ld_wait();
+                        float4 x[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b4 = *reinterpret_cast<const float4 *>(bz + s * TC_KC + 16 * pc + 4 * q);
+                            x[q].x = fmaxf(fmaf(__uint_as_float(v[4 * q + 0]), inv, b4.x), 0.f);
+                            x[q].y = fmaxf(fmaf(__uint_as_float(v[4 * q + 1]), inv, b4.y), 0.f);
+                            x[q].z = fmaxf(fmaf(__uint_as_float(v[4 * q + 2]), inv, b4.z), 0.f);
+                            x[q].w = fmaxf(fmaf(__uint_as_float(v[4 * q + 3]), inv, b4.w), 0.f);
+                        }
+                        // overlap the next TMEM read: next piece of this slab, else the group's next slab
+                        if (pc + 1 < PIECES) tmem_ld_32x16(tsrc + (uint32_t)(TC_KC * s + 16 * (pc + 1)), v);
+                        else if (s + TC_GROUPS < nslab) tmem_ld_32x16(tsrc + (uint32_t)(TC_KC * (s + TC_GROUPS)), v);
+                        store16(base + s, pc, x);
+                    }
                     release(base + s);
                 }
                 base += nslab;
-                bias_off += NPAD(l - 1);
+                bias_off += NPAD(l - 1) + TC_BIAS_PAD;
                 TC_STAMP(20 + l);
             }
             // ---------------- last epilogue: the groups alternate 16-column chunks ----------------
@@ -459,6 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
                 ++dl;
                 tcgen05_fence_after();
                 TC_STAMP(30);
+                const float inv = bias_s[bias_off + npad];   // 1 / weight scale of the last layer
                 uint32_t v[16];
                 int c0 = 16 * g;
                 if (c0 < npad) tmem_ld_32x16(tsrc + (uint32_t)c0, v);
@@ -468,19 +554,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
                     float x[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float t = __uint_as_float(v[j]) + bias_s[bias_off + c0 + j];
+                        const float t = fmaf(__uint_as_float(v[j]), inv, bias_s[bias_off + c0 + j]);
                         x[j] = a.relu_last ? fmaxf(t, 0.f) : t;
                     }
                     if (c0 + 16 * TC_GROUPS < npad) tmem_ld_32x16(tsrc + (uint32_t)(c0 + 16 * TC_GROUPS), v);
                     if (a.group > 0) {
-                        // max over the 32 rows of this warp, column by column; lane j keeps column c0+j
-                        uint32_t keep = 0;
+                        // max over the 32 rows of this warp for each of the 16 columns
+                        if (!valid) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const uint32_t m = __reduce_max_sync(kFull, valid ? __float_as_uint(x[j]) : 0u);
-                            if (lane == j) keep = m;
+                            for (int j = 0; j < 16; ++j) x[j] = -INFINITY;
                         }
-                        if (lane < 16) red[(warp & 3) * 256 + c0 + lane] = __uint_as_float(keep);
+                        int col;
+                        const float m = warp_colmax16(x, lane, col);
+                        if (lane < 16) red[(warp & 3) * 256 + c0 + col] = m;
                     } else if (valid) {
                         float *dst = a.out + grow * a.ldo + col_off + c0;
                         if (c0 + 16 <= cout_last && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -519,27 +605,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
     if (warp == TC_PROD / 32) tmem_dealloc_dyn(tmem_base, (uint32_t)a.tmem_cols);
 }
 
-// weights -> [slab][plane hi|lo][8 chunks][npad][4], pre-split, zero padded; bias -> [npad]
-__global__ void pack_tc_kernel(int cin, int cout, int kpad, int npad, const float *__restrict__ w,
-                               const float *__restrict__ bias, float *__restrict__ wpk, float *__restrict__ bp) {
-    const int nslab = kpad / TC_KC;
-    const int plane = TC_NCHUNK * npad * 4;          // floats per plane
-    const int total = nslab * plane;                 // one thread per (slab, chunk, n, e) -> writes hi and lo
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int e = i & 3;
-        const int n = (i >> 2) % npad;
-        const int q = ((i >> 2) / npad) % TC_NCHUNK;
-        const int s = (i >> 2) / npad / TC_NCHUNK;
-        const int k = s * TC_KC + q * 4 + e;
-        const float v = (k < cin && n < cout) ? w[(size_t)n * cin + k] : 0.f;
-        float hi, lo;
-        split_tf32(v, hi, lo);
-        const size_t o = (size_t)s * 2 * plane + ((size_t)q * npad + n) * 4 + e;
-        wpk[o] = hi;
-        wpk[o + plane] = lo;
+// bias -> [npad + 16]: bias, then 1/scale at [npad] and scale at [npad+1].  The weight scale is a power of
+// two that brings max|W| of the layer into [2^12, 2^13) for fp16 operands (1 for TF32).
+__global__ void tc_scale_kernel(int cin, int cout, int npad, int f16, const float *__restrict__ w,
+                                const float *__restrict__ bias, float *__restrict__ bp) {
+    __shared__ float red[256];
+    float m = 0.f;
+    for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
     }
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < npad; c += gridDim.x * blockDim.x)
-        bp[c] = (c < cout && bias) ? bias[c] : 0.f;
+    for (int c = threadIdx.x; c < npad + TC_BIAS_PAD; c += blockDim.x) bp[c] = (c < cout && bias) ? bias[c] : 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float scale = 1.f;
+        if (f16 && red[0] > 0.f && isfinite(red[0])) {
+            int e;
+            frexpf(red[0], &e);                 // red[0] = f * 2^e, f in [0.5, 1)
+            scale = ldexpf(1.f, 13 - e);        // max|W| * scale in [2^12, 2^13)
+        }
+        bp[npad] = 1.f / scale;
+        bp[npad + 1] = scale;
+    }
+}
+
+// weights -> [slab][plane hi|lo][8 chunks][npad][16 bytes], pre-split, zero padded
+template <bool F16>
+__global__ void pack_tc_kernel(int cin, int cout, int kpad, int npad, const float *__restrict__ w,
+                               const float *__restrict__ bp, float *__restrict__ wpk) {
+    constexpr int KC = tc_kc(F16), EPC = F16 ? 8 : 4;          // channels per slab / elements per 16-byte chunk
+    const int nslab = kpad / KC;
+    const int plane_bytes = TC_NCHUNK * npad * 16;
+    const float scale = bp[npad + 1];
+    const int total = nslab * TC_NCHUNK * npad * EPC;          // one thread per element -> writes hi and lo
+    uint8_t *out = reinterpret_cast<uint8_t *>(wpk);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int e = i % EPC;
+        const int n = (i / EPC) % npad;
+        const int q = (i / EPC / npad) % TC_NCHUNK;
+        const int s = i / EPC / npad / TC_NCHUNK;
+        const int k = s * KC + q * EPC + e;
+        const float v = (k < cin && n < cout) ? w[(size_t)n * cin + k] * scale : 0.f;
+        const size_t o = (size_t)s * 2 * plane_bytes + ((size_t)q * npad + n) * 16;
+        if (F16) {
+            unsigned short hi, lo;
+            split_f16(v, hi, lo);
+            reinterpret_cast<unsigned short *>(out + o)[e] = hi;
+            reinterpret_cast<unsigned short *>(out + o + plane_bytes)[e] = lo;
+        } else {
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            reinterpret_cast<float *>(out + o)[e] = hi;
+            reinterpret_cast<float *>(out + o + plane_bytes)[e] = lo;
+        }
+    }
 }
 
 struct TcLayout {
@@ -557,7 +679,8 @@ static int pow2_at_least(int v, int lo) {
     return p;
 }
 
-static TcLayout tc_layout(const captra_mlp_desc &d) {
+static TcLayout tc_layout(const captra_mlp_desc &d, bool f16) {
+    const int TC_KC = tc_kc(f16);
     TcLayout L{};
     L.nlayers = d.nlayers;
     L.supported = true;
@@ -577,9 +700,11 @@ static TcLayout tc_layout(const captra_mlp_desc &d) {
             }
         }
         npmax = max(npmax, min(L.npad[l], 256));
-        L.off_w[l] = off; off += (size_t)L.kpad[l] * L.npad[l] * 2;
-        L.off_b[l] = off; off += L.npad[l];
-        L.bias_floats += L.npad[l];
+        // packed weights of a layer: nslab * 2 planes * 8 chunks * npad * 16 bytes (in floats: /4)
+        L.off_w[l] = off; off += (size_t)(L.kpad[l] / TC_KC) * 2 * TC_NCHUNK * L.npad[l] * 4;
+        const int nb = L.nsplit > 1 ? L.nsplit * (256 + TC_BIAS_PAD) : L.npad[l] + TC_BIAS_PAD;
+        L.off_b[l] = off; off += nb;
+        L.bias_floats += nb;
         cin = L.npad[l];           // the next layer sees the padded width (zero weights on the pad)
     }
     L.total_floats = off;
@@ -597,15 +722,14 @@ static TcLayout tc_layout(const captra_mlp_desc &d) {
     return L;
 }
 
-int64_t tc_pack_bytes(const captra_mlp_desc *d) {
-    const TcLayout L = tc_layout(*d);
+int64_t tc_pack_bytes(const captra_mlp_desc *d, bool f16) {
+    const TcLayout L = tc_layout(*d, f16);
     return L.supported ? (int64_t)(L.total_floats * sizeof(float)) : -1;
 }
 
-bool tc_supported(const captra_mlp_desc *d) { return tc_layout(*d).supported; }
-
-int tc_pack(const captra_mlp_desc *d, void *packed, cudaStream_t stream) {
-    const TcLayout L = tc_layout(*d);
+int tc_pack(const captra_mlp_desc *d, void *packed, bool f16, cudaStream_t stream) {
+    const TcLayout L = tc_layout(*d, f16);
+    const int KC = tc_kc(f16);
     CAPTRA_REQUIRE(L.supported, "mlp_pack(tc): layer widths not supported by the tcgen05 path");
     int cin = d->cin;      // true input width of layer l (the packed K is zero padded to L.kpad[l])
     for (int l = 0; l < d->nlayers; ++l) {
@@ -613,10 +737,13 @@ int tc_pack(const captra_mlp_desc *d, void *packed, cudaStream_t stream) {
         for (int y = 0; y < L.nsplit; ++y) {   // nsplit > 1 only for a single wide layer
             const int npad_y = L.nsplit == 1 ? L.npad[l] : (y < L.nsplit - 1 ? 256 : L.last_npad);
             const int cout_y = L.nsplit == 1 ? d->cout[l] : min(256, d->cout[l] - 256 * y);
-            pack_tc_kernel<<<64, 256, 0, stream>>>(cin, cout_y, L.kpad[l], npad_y, d->w[l] + (size_t)y * 256 * cin,
-                                                   d->bias[l] ? d->bias[l] + y * 256 : nullptr,
-                                                   base + L.off_w[l] + (size_t)y * L.kpad[l] * 256 * 2,
-                                                   base + L.off_b[l] + y * 256);
+            const float *w_y = d->w[l] + (size_t)y * 256 * cin;
+            float *bp = base + L.off_b[l] + (size_t)y * (256 + TC_BIAS_PAD);
+            float *wp = base + L.off_w[l] + (size_t)y * (L.kpad[l] / KC) * 2 * TC_NCHUNK * 256 * 4;
+            tc_scale_kernel<<<1, 256, 0, stream>>>(cin, cout_y, npad_y, f16 ? 1 : 0, w_y, d->bias[l] ? d->bias[l] + y * 256 : nullptr, bp);
+            CAPTRA_CHECK_LAUNCH("mlp_pack(tc scale)");
+            if (f16) pack_tc_kernel<true><<<64, 256, 0, stream>>>(cin, cout_y, L.kpad[l], npad_y, w_y, bp, wp);
+            else pack_tc_kernel<false><<<64, 256, 0, stream>>>(cin, cout_y, L.kpad[l], npad_y, w_y, bp, wp);
             CAPTRA_CHECK_LAUNCH("mlp_pack(tc)");
         }
         cin = d->cout[l];
@@ -624,8 +751,9 @@ int tc_pack(const captra_mlp_desc *d, void *packed, cudaStream_t stream) {
     return CAPTRA_OK;
 }
 
-static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, size_t *smem) {
-    const TcLayout L = tc_layout(*d);
+static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool f16, size_t *smem) {
+    const TcLayout L = tc_layout(*d, f16);
+    a.f16 = f16 ? 1 : 0;
     CAPTRA_REQUIRE(L.supported, "mlp(tc): layer widths not supported by the tcgen05 path");
     a.nlayers = d->nlayers; a.relu_last = d->relu_last; a.cout_last = d->cout[d->nlayers - 1];
     for (int l = 0; l < d->nlayers; ++l) {
@@ -636,35 +764,41 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, size
     a.wstage_bytes = L.wstage_bytes; a.bias_floats = L.bias_floats;
     a.region_cols = L.region_cols; a.tmem_cols = L.tmem_cols; a.nst_log2 = L.nstages == 4 ? 2 : 1;
     a.nsplit = L.nsplit; a.last_npad = L.last_npad; a.cout_total = d->cout[d->nlayers - 1];
+    {
+        const int kc = tc_kc(f16), kmma = f16 ? 16 : 8;
+        a.cin0 = d->cin;
+        const int rem = d->cin - (L.kpad[0] / kc - 1) * kc;     // channels in layer 0's last slab
+        a.klast0 = ceil_div(rem, kmma);
+    }
     { const char *e = getenv("CAPTRA_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
     *smem = L.smem_bytes;
     return CAPTRA_OK;
 }
 
-template <int MODE>
-static int tc_launch(TcArgs &a, size_t smem, cudaStream_t stream) {
-    auto kern = mlp_tc_kernel<MODE>;
+template <int MODE, bool F16>
+static int tc_launch_t(TcArgs &a, size_t smem, cudaStream_t stream) {
+    auto kern = mlp_tc_kernel<MODE, F16>;
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
-    int occ = 1;
-    CAPTRA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TC_THREADS, smem));
-    occ = max(1, min(occ, 512 / a.tmem_cols));      // co-resident CTAs also share the 512 TMEM columns
-    const int64_t slots = (int64_t)max(1, sm_count() / a.nsplit) * occ;
+    const int64_t slots = (int64_t)max(1, sm_count() / a.nsplit);     // one CTA per SM
     const int gx = (int)(a.ntiles < slots ? a.ntiles : slots);
     kern<<<dim3(gx, a.nsplit), TC_THREADS, smem, stream>>>(a);
     CAPTRA_CHECK_LAUNCH("mlp_tc");
     return CAPTRA_OK;
 }
+template <int MODE>
+static int tc_launch(TcArgs &a, size_t smem, cudaStream_t stream) {
+    return a.f16 ? tc_launch_t<MODE, true>(a, smem, stream) : tc_launch_t<MODE, false>(a, smem, stream);
+}
 
 int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const float *new_xyz,
                   const float *feats, const int *idx, const captra_mlp_desc *d, const void *packed,
-                  float *out, int64_t ldo, int col_off, cudaStream_t stream) {
+                  float *out, int64_t ldo, int col_off, bool f16, cudaStream_t stream) {
     CAPTRA_REQUIRE(k == 32 || k == 64 || k == 128, "sa_mlp_max(tc): nsample must be 32, 64 or 128 (got %d)", k);
     CAPTRA_REQUIRE(d->relu_last, "sa_mlp_max(tc): the max epilogue needs a ReLU after the last layer");
     TcArgs a{};
     size_t smem;
-    int rc = tc_fill(a, d, packed, &smem);
+    int rc = tc_fill(a, d, packed, f16, &smem);
     if (rc) return rc;
     a.rows = (int64_t)b * s * k; a.group = k;
     a.out = out; a.ldo = ldo; a.col_off = col_off;
@@ -674,13 +808,13 @@ int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const
 
 static int tc_point_mlp_ex(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
                            int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
-                           int group, cudaStream_t stream, const float *in_scale, const float *in_shift,
+                           int group, bool f16, cudaStream_t stream, const float *in_scale, const float *in_shift,
                            int rows_per_cloud) {
     CAPTRA_REQUIRE(group == 0 || ((group == 32 || group == 64 || group == 128) && d->relu_last),
                    "point_mlp(tc): grouped max needs group in {32,64,128} and a final ReLU");
     TcArgs a{};
     size_t smem;
-    int rc = tc_fill(a, d, packed, &smem);
+    int rc = tc_fill(a, d, packed, f16, &smem);
     if (rc) return rc;
     a.rows = rows; a.group = group;
     a.out = y; a.ldo = ldy; a.col_off = col_off;
@@ -691,8 +825,8 @@ static int tc_point_mlp_ex(int64_t rows, const float *segA, int64_t ldA, int ca,
 
 int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
                  int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
-                 int group, cudaStream_t stream) {
-    return tc_point_mlp_ex(rows, segA, ldA, ca, segB, ldB, cb, bcast, d, packed, y, ldy, col_off, group, stream, nullptr, nullptr, 0);
+                 int group, bool f16, cudaStream_t stream) {
+    return tc_point_mlp_ex(rows, segA, ldA, ca, segB, ldB, cb, bcast, d, packed, y, ldy, col_off, group, f16, stream, nullptr, nullptr, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -775,8 +909,8 @@ extern "C" int captra_group_norm_affine(int clouds, int npts, int c, int channel
 namespace captra {
 int tc_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale, const float *in_shift,
                         int rows_per_cloud, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
-                        int col_off, cudaStream_t stream) {
-    return tc_point_mlp_ex(rows, x, ldx, cin, nullptr, 0, 0, 0, d, packed, y, ldy, col_off, 0, stream, in_scale, in_shift, rows_per_cloud);
+                        int col_off, bool f16, cudaStream_t stream) {
+    return tc_point_mlp_ex(rows, x, ldx, cin, nullptr, 0, 0, 0, d, packed, y, ldy, col_off, 0, f16, stream, in_scale, in_shift, rows_per_cloud);
 }
 }  // namespace captra
 

@@ -13,7 +13,9 @@ import torch
 from . import _lib
 
 MAX_LAYERS = 4
-# 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel (default).  CAPTRA_MLP_IMPL overrides.
+# 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel (default), 2 = tcgen05 fp16x3 kernel
+# (same split arithmetic on fp16 operands: half the operand bytes, K=16 per MMA; activations
+# saturate at 65504).  CAPTRA_MLP_IMPL overrides.
 DEFAULT_IMPL = int(os.environ.get("CAPTRA_MLP_IMPL", "1"))
 
 
@@ -72,25 +74,25 @@ class PackedMLP:
         # on the same tcgen05 kernel, a wide layer split into 256-column chunks over grid.y; the
         # [rows, cout] intermediates are a few MB and stay in L2.
         self._layers = None
-        if self.impl == 1 and len(weights) > 1 and not self._tc_supported():
+        if self.impl in (1, 2) and len(weights) > 1 and not self._tc_supported():
             n = len(weights)
-            self._layers = [PackedMLP([self._w[l]], [self._b[l]], relu_last=(l < n - 1 or self.relu_last), impl=1)
+            self._layers = [PackedMLP([self._w[l]], [self._b[l]], relu_last=(l < n - 1 or self.relu_last), impl=self.impl)
                             for l in range(n)]
         else:
             self._pack(self._pick(self.impl))
 
     def _tc_supported(self):
         if self._tc_ok is None:
-            self._tc_ok = _lib.load().captra_mlp_pack_bytes(ctypes.byref(self.desc), 1) >= 0
+            self._tc_ok = _lib.load().captra_mlp_pack_bytes(ctypes.byref(self.desc), self.impl if self.impl in (1, 2) else 1) >= 0
         return self._tc_ok
 
     def _pick(self, impl, group=0, sa=False):
-        if impl == 1 and self._tc_supported():
+        if impl in (1, 2) and self._tc_supported():
             if sa and (group not in self.TC_GROUPS or not self.relu_last):
                 return 0
             if not sa and group and (group not in self.TC_GROUPS or not self.relu_last):
                 return 0
-            return 1
+            return impl
         return 0
 
     def _pack(self, impl):
@@ -158,15 +160,16 @@ class PackedMLP:
         row r of cloud b = r // rows_per_cloud enters as relu(x[r] * scale[b] + shift[b])
         (GroupNorm + ReLU of the producer layer, see group_norm_affine).  tcgen05 path only."""
         f32 = torch.float32
-        if self._pick(1) != 1 or self._layers is not None:
+        impl = self._pick(self.impl)
+        if impl not in (1, 2) or self._layers is not None:
             raise _lib.CaptraError("rows_affine needs a chain the fused tcgen05 kernel supports")
         R, cin = x.shape
         if out is None:
             out = torch.empty(R, self.cout, dtype=f32, device=self.device)
-        _lib.call("point_mlp[R=%d,C=%d->%s,g=0,impl=1,affine]" % (R, self.cin, "-".join(map(str, self.couts))),
+        _lib.call("point_mlp[R=%d,C=%d->%s,g=0,impl=%d,affine]" % (R, self.cin, "-".join(map(str, self.couts)), impl),
                   _lib.load().captra_point_mlp_affine, R, _lib.ptr(x, f32, "x"), x.stride(0), cin,
                   _lib.ptr(scale, f32, "scale"), _lib.ptr(shift, f32, "shift"), rows_per_cloud,
-                  ctypes.byref(self.desc), self._pack(1).data_ptr(), _lib.ptr(out, f32, "out"), out.shape[-1], col_off, 1,
+                  ctypes.byref(self.desc), self._pack(impl).data_ptr(), _lib.ptr(out, f32, "out"), out.shape[-1], col_off, impl,
                   _lib.stream_ptr(self.device), device=self.device)
         return out
 

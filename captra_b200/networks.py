@@ -118,7 +118,7 @@ class MLPConv1d(nn.Module):
         if not hasattr(self, "_cache"):
             self._cache = _FusedCache()
         packs = self._cache.get(self, lambda: [PackedMLP([c.weight.detach().reshape(c.out_channels, c.in_channels)],
-                                                         [c.bias.detach()], relu_last=False, impl=1) for c in convs])
+                                                         [c.bias.detach()], relu_last=False, impl=_mlp.DEFAULT_IMPL) for c in convs])
         y = packs[0].rows(feat_pm.reshape(B * N, C))
         for i in range(1, len(convs)):
             scale, shift = group_norm_affine(y, B, N, gns[i - 1])
@@ -206,7 +206,7 @@ class RotationRegressionBackbone(nn.Module):
         copy p, masked mean over part p's points (networks.py:127-139 restricted to the diagonal
         that networks.py:200-203 keeps)."""
         P = self.num_parts
-        fused = _mlp.DEFAULT_IMPL == 1 and not _needs_autograd(self, cam)
+        fused = _mlp.DEFAULT_IMPL in (1, 2) and not _needs_autograd(self, cam)
         if fused:
             feat_pm = self.encoder.forward_pm(cam)                 # [B*P, N, C] point-major
             feat_pm = feat_pm.reshape(batch_size, P, feat_pm.shape[1], feat_pm.shape[2])

@@ -23,7 +23,7 @@ def mk(cin, couts):
         ws.append((torch.randn(c, last, generator=gen) / last ** 0.5).to(dev))
         bs.append((0.1 * torch.randn(c, generator=gen)).to(dev))
         last = c
-    return PackedMLP(ws, bs, impl=1)
+    return PackedMLP(ws, bs, impl=int(os.environ.get('PROBE_IMPL', '1')))
 
 
 cases = []
@@ -40,7 +40,7 @@ cases.append(("sa2 K=64 323->128-128-256", mk(323, [128, 128, 256]), c1, c2, f2,
 
 for name, mlp, xyz, ctr, feats, idx in cases:
     out = torch.empty(B, ctr.shape[1], mlp.cout, device=dev)
-    for dbg in (0, 4, 15):
+    for dbg in (0,):
         os.environ["CAPTRA_TC_DBG"] = str(dbg)
         for _ in range(2):
             mlp.sa_max(xyz, ctr, feats, idx, out)
@@ -69,7 +69,7 @@ for name, mlp, xyz, ctr, feats, idx in cases:
         ts = [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
         print(name, "dbg", dbg, "stamps", n)
         line = []
-        for i in range(1, min(n, 30)):
+        for i in range(1, min(n, 19)):
             line.append("%d->%d:%d" % (ts[i - 1][1], ts[i][1], ts[i][0] - ts[i - 1][0]))
         print("  " + "  ".join(line))
 os.environ["CAPTRA_TC_DBG"] = "0"

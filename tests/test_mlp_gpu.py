@@ -14,7 +14,7 @@ from captra_b200 import synthetic
 
 pytestmark = pytest.mark.gpu
 TOL = dict(rtol=1e-4, atol=1e-5)
-IMPLS = [0, 1]
+IMPLS = [0, 1, 2]
 
 
 @pytest.fixture(autouse=True)
@@ -187,10 +187,18 @@ def test_rotation_head_groupnorm_fused_vs_torch(cuda):
             m.bias.data.normal_(0, 0.2)
     B, N = 3, 4096
     feat = torch.randn(B, 128, N, device=cuda)
+    from captra_b200 import mlp
     with torch.no_grad():
         want = head(feat)                                            # [B, 6, N]
-        got = head.forward_pm(feat.transpose(1, 2).contiguous()).transpose(1, 2)
-    torch.testing.assert_close(got, want, rtol=1e-3, atol=2e-4)      # 3xTF32 through 4 layers + GroupNorm
+        for impl in (1, 2):
+            mlp.DEFAULT_IMPL, old = impl, mlp.DEFAULT_IMPL
+            head.__dict__.pop("_cache", None)            # re-pack for this impl
+            try:
+                got = head.forward_pm(feat.transpose(1, 2).contiguous()).transpose(1, 2)
+            finally:
+                mlp.DEFAULT_IMPL = old
+            head.__dict__.pop("_cache", None)
+            torch.testing.assert_close(got, want, rtol=1e-3, atol=2e-4)  # split-precision GEMMs through 4 layers + GroupNorm
 
 
 def test_group_norm_affine_kernel(cuda):

@@ -57,7 +57,7 @@ def _make_nocs_meaningful(coordnet, num_parts):
                 last.weight[3 * p + i, 3 + i] = -4.0
 
 
-@pytest.fixture(params=[0, 1])
+@pytest.fixture(params=[0, 1, 2])
 def impl(request, monkeypatch):
     from captra_b200 import mlp
     monkeypatch.setattr(mlp, "DEFAULT_IMPL", request.param)
