@@ -208,6 +208,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=4, help="clouds per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
@@ -234,7 +235,7 @@ def main():
     torch.cuda.set_device(dev)
     torch.backends.cuda.matmul.allow_tf32 = False   # heads are torch fp32; keep them true fp32 like the reference
     torch.backends.cudnn.allow_tf32 = False
-    from captra_b200 import _lib, shard, track
+    from captra_b200 import _lib, mlp, shard, track
     _lib.load()
     cfg = track.make_cfg(w["category"], device=str(dev))
     trk = track.Tracker(cfg, seed=0).to(dev).eval()
@@ -252,9 +253,20 @@ def main():
         """pose-error sums a tracker logs per batch (test.py:87-99 in spirit): sums + count."""
         return shard.pose_error_scalars(pose, gt)
 
+    # the whole frame as one CUDA graph (falls back to eager launches if capture is not possible)
+    step_fn, graph_note, graph_launches = trk.step, "eager launches", None
+    if not args.no_graph:
+        try:
+            r0 = resident[0]
+            gs = track.GraphedStep(trk, r0["points"], r0["mean"], r0["pose"])
+            step_fn, graph_note, graph_launches = gs, "one CUDA graph per frame", gs.launches_per_replay
+        except Exception as e:  # noqa: BLE001
+            graph_note = "eager launches (graph capture failed: %s)" % str(e).splitlines()[0][:120]
+            torch.cuda.synchronize(dev)
+
     def step_resident(i):
         r = resident[i % nb]
-        pose = trk.step(r["points"], r["mean"], r["pose"])
+        pose = step_fn(r["points"], r["mean"], r["pose"])
         ls = shard.all_reduce_scalars(loss_scalars(pose, pinned[i % nb]["gt"]))
         return pose, ls
 
@@ -282,6 +294,8 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = _lib.launch_count() - l0
+    if graph_launches is not None:          # replayed kernels do not pass through the C ABI again
+        launches = graph_launches * args.steps
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(np.sum(step_ms))
 
@@ -292,10 +306,13 @@ def main():
 
     def step_e2e(i):
         p = pinned[i % nb]
-        pts = p["points"].to(dev, non_blocking=True)
-        mean = p["mean"].to(dev, non_blocking=True)
-        pose = {k: v.to(dev, non_blocking=True) for k, v in p["pose"].items()}
-        new = trk.step(pts, mean, pose)
+        if graph_launches is not None:      # H2D straight into the graph's static input buffers
+            new = step_fn(p["points"], p["mean"], p["pose"])
+        else:
+            pts = p["points"].to(dev, non_blocking=True)
+            mean = p["mean"].to(dev, non_blocking=True)
+            pose = {k: v.to(dev, non_blocking=True) for k, v in p["pose"].items()}
+            new = trk.step(pts, mean, pose)
         shard.all_reduce_scalars(loss_scalars(new, p["gt"]))
         for k in out_host:
             out_host[k].copy_(new[k], non_blocking=True)
@@ -367,6 +384,7 @@ def main():
                        "ms_per_step": qg_ms, "gbs": qg_bytes / (qg_ms * 1e-3) / 1e9 if qg_ms else 0.0,
                        "frac_of_hbm_peak": (qg_bytes / (qg_ms * 1e-3) / 1e9) / pk["hbm"] if qg_ms else 0.0}
 
+    overflow = mlp.f16_overflowed() if mlp.DEFAULT_IMPL == 2 else None
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -381,7 +399,7 @@ def main():
         "metric": METRIC, "value": frames / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
-                                            mlp_impl=int(os.environ.get("CAPTRA_MLP_IMPL", "1")),
+                                            mlp_impl={0: "fp32 CUDA cores", 1: "tcgen05 3xTF32", 2: "tcgen05 fp16x3 (fp32 accumulate, overflow-checked)"}[mlp.DEFAULT_IMPL], launch=graph_note, f16_overflow=overflow,
                                             heads="fused: tcgen05 GEMMs + GroupNorm folded into the operand load (impl 1); torch modules for impl 0", collective="nccl all_reduce of 4 pose-error scalars per step" if world > 1 else "none"),
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},

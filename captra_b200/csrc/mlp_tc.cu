@@ -127,7 +127,7 @@ constexpr int TC_THREADS = TC_PROD + 64;          // + MMA warp (8) + TMA warp (
 // parts stay normal, activations saturate at +-65504).
 constexpr int TC_NCHUNK = 8;
 constexpr int TC_BIAS_PAD = 16;                   // bias region = npad + 16 floats; [npad] = 1 / weight scale
-__host__ __device__ constexpr int tc_kc(bool f16) { return f16 ? 64 : 32; }
+__host__ __device__ constexpr int tc_kc(bool f16, bool small) { return (f16 ? 64 : 32) / (small ? 2 : 1); }
 constexpr int TC_A_PLANE = TC_NCHUNK * TC_CHUNK_BYTES;   // bytes of one (hi or lo) A slab plane: 16 KB
 constexpr int TC_A_STAGE = 2 * TC_A_PLANE;        // hi + lo
 constexpr int TC_MAX_STAGES = 4;
@@ -145,7 +145,7 @@ struct TcArgs {
     const float *in_scale, *in_shift; int rows_per_cloud;   // dense: x <- relu(x * scale[cloud] + shift[cloud]) on load (GroupNorm + ReLU of the producer layer)
     int wstage_bytes, bias_floats, region_cols, tmem_cols, nst_log2;
     int nsplit, last_npad, cout_total;          // single wide layer split into 256-column chunks over grid.y
-    int f16;
+    int f16, small;
     int cin0, klast0;                           // true layer-0 width; k-steps that carry data in layer 0's last slab
     int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A stores, 2 no W copies, 4 no MMAs, 8 no last epilogue, 32/128 stamps, 64 no gather
 };
@@ -165,7 +165,10 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// x -> (hi, lo) as fp16 with saturation; returns hi | lo<<16 is NOT what we want: planes are separate
+// fp16 operands saturate at +-65504.  A value that large is recorded in g_f16_overflow so the host can
+// detect the (never observed) case and re-run on the 3xTF32 path (captra_f16_overflow_flag).
+__device__ int g_f16_overflow;
+// x -> (hi, lo) as two fp16 numbers (hi = rn(x), lo = rn(x - hi)): 22 mantissa bits together
 __device__ __forceinline__ void split_f16(float x, unsigned short &hi, unsigned short &lo) {
     unsigned short h, l;
     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
@@ -228,9 +231,21 @@ __device__ int g_tc_ts_n;
 // per barrier round), ONE `full` barrier per stage shared by the A producers and the weight TMA
 // (4 warp arrivals + 1 arrive.expect_tx), descriptors advanced by adding to their low word, and
 // two producer groups that alternate slabs so their per-slab latency chains overlap.
-template <int MODE, bool F16>  // MODE 0: SA gather loader, 1: dense-row loader; the last epilogue is chosen by a.group
-__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
-    constexpr int TC_KC = tc_kc(F16);
+//
+// Two shapes of the same kernel.  LARGE (wide layers): 320 threads, two producer groups alternating
+// 8-chunk slabs, one CTA per SM.  SMALL (every layer <= 128 columns: the sa1 scales, fp1): the tile
+// time is a chain of latencies (gather, MMA drain, TMEM read, epilogue), not throughput, so the CTA
+// shrinks to one producer group and 4-chunk slabs (192 threads, 64 KB, 256 TMEM columns) and TWO CTAs
+// share an SM, each on its own tile.
+template <int MODE, bool F16, bool SMALL>  // MODE 0: SA gather loader, 1: dense-row loader; the last epilogue is chosen by a.group
+__global__ void __launch_bounds__(SMALL ? 192 : 320, SMALL ? 2 : 1) mlp_tc_kernel(const TcArgs a) {
+    constexpr int TC_GROUPS = SMALL ? 1 : 2;
+    constexpr int TC_PROD = 128 * TC_GROUPS;
+    constexpr int TC_THREADS = TC_PROD + 64;
+    constexpr int TC_NCHUNK = SMALL ? 4 : 8;
+    constexpr int TC_A_PLANE = TC_NCHUNK * TC_CHUNK_BYTES;
+    constexpr int TC_A_STAGE = 2 * TC_A_PLANE;
+    constexpr int TC_KC = tc_kc(F16, SMALL);
     constexpr int PIECES = TC_KC / 16;             // 16-channel pieces per slab
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], d_ready;
@@ -350,6 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         uint32_t base = 0;                    // global index of the current layer's slab 0
         uint32_t dl = 0;
+        float amax = 0.f;                     // largest |operand| this thread converted to fp16
 
         auto warp_wait = [&](uint64_t *bar, uint32_t parity) {   // one lane polls, the warp follows
             if (lane == 0) mbar_wait(bar, parity);
@@ -367,7 +383,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
                     const float e[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
                     unsigned short hh[8], ll[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) split_f16(e[j], hh[j], ll[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        split_f16(e[j], hh[j], ll[j]);
+                        amax = fmaxf(amax, fabsf(e[j]));      // saturation watch, checked once per tile
+                    }
                     const int chunk = 2 * pc + q;
                     *reinterpret_cast<uint4 *>(plane_hi + chunk * (TC_ROWS * 4)) =
                         make_uint4(pack2(hh[0], hh[1]), pack2(hh[2], hh[3]), pack2(hh[4], hh[5]), pack2(hh[6], hh[7]));
@@ -583,7 +602,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
                 if (a.group > 0) {
                     // combine the per-warp maxima of the warps that share a group and write them out
                     const int wpg = a.group / 32;                 // row-warps per group: 1, 2 or 4
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
                     const int ngroups = 4 / wpg;
                     for (int o = tid; o < ngroups * npad; o += TC_PROD) {
                         const int gi = o / npad, c = o - gi * npad;
@@ -593,12 +612,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcArgs a) {
                         for (int w = 1; w < wpg; ++w) m = fmaxf(m, red[(gi * wpg + w) * 256 + c]);
                         a.out[cen * a.ldo + col_off + c] = m;
                     }
-                    asm volatile("bar.sync 1, 256;" ::: "memory");   // red aliases a_stage[0]
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");   // red aliases a_stage[0]
                 }
                 tcgen05_fence_before();
                 TC_STAMP(31);
             }
         }
+        if (F16 && !(amax < 65000.f)) g_f16_overflow = 1;   // also catches NaN
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -634,9 +654,10 @@ __global__ void tc_scale_kernel(int cin, int cout, int npad, int f16, const floa
 
 // weights -> [slab][plane hi|lo][8 chunks][npad][16 bytes], pre-split, zero padded
 template <bool F16>
-__global__ void pack_tc_kernel(int cin, int cout, int kpad, int npad, const float *__restrict__ w,
+__global__ void pack_tc_kernel(int cin, int cout, int kpad, int npad, int nchunk, const float *__restrict__ w,
                                const float *__restrict__ bp, float *__restrict__ wpk) {
-    constexpr int KC = tc_kc(F16), EPC = F16 ? 8 : 4;          // channels per slab / elements per 16-byte chunk
+    constexpr int EPC = F16 ? 8 : 4;                           // elements per 16-byte chunk
+    const int TC_NCHUNK = nchunk, KC = nchunk * EPC;           // chunks / channels per slab
     const int nslab = kpad / KC;
     const int plane_bytes = TC_NCHUNK * npad * 16;
     const float scale = bp[npad + 1];
@@ -670,7 +691,8 @@ struct TcLayout {
     int wstage_bytes, bias_floats, nsplit, last_npad;
     int nstages, region_cols, tmem_cols, target_occ;
     size_t smem_bytes;
-    bool supported;
+    bool supported, small;
+    int nchunk;
 };
 
 static int pow2_at_least(int v, int lo) {
@@ -679,9 +701,12 @@ static int pow2_at_least(int v, int lo) {
     return p;
 }
 
-static TcLayout tc_layout(const captra_mlp_desc &d, bool f16) {
-    const int TC_KC = tc_kc(f16);
+static TcLayout tc_layout_v(const captra_mlp_desc &d, bool f16, bool small) {
+    const int TC_KC = tc_kc(f16, small);
+    const int TC_NCHUNK = small ? 4 : 8;
+    const int TC_A_STAGE = 2 * TC_NCHUNK * TC_CHUNK_BYTES;
     TcLayout L{};
+    L.small = small; L.nchunk = TC_NCHUNK;
     L.nlayers = d.nlayers;
     L.supported = true;
     L.nsplit = 1;
@@ -713,13 +738,21 @@ static TcLayout tc_layout(const captra_mlp_desc &d, bool f16) {
     L.region_cols = pow2_at_least(npmax, 32);
     L.tmem_cols = d.nlayers > 1 ? 2 * L.region_cols : L.region_cols;
     L.target_occ = 1;
-    // 4 pipeline stages if they fit in 227 KB, else 2
+    // LARGE: 4 pipeline stages if they fit in 227 KB, else 2.  SMALL: 2 stages, two CTAs per SM.
     const size_t fixed = (size_t)L.bias_floats * 4 + 256;
     const size_t per_stage = (size_t)TC_A_STAGE + L.wstage_bytes;
-    L.nstages = (fixed + 4 * per_stage <= 225 * 1024) ? 4 : 2;
+    const size_t budget = small ? (size_t)(227 * 1024) / 2 - 2048 : (size_t)225 * 1024;
+    L.nstages = (!small && fixed + 4 * per_stage <= budget) ? 4 : 2;
     L.smem_bytes = fixed + (size_t)L.nstages * per_stage;
-    if (L.smem_bytes > 225 * 1024) L.supported = false;
+    if (L.smem_bytes > budget) L.supported = false;
+    if (small && (d.nlayers < 2 || npmax > 128)) L.supported = false;
     return L;
+}
+
+// fused chains whose layers are all <= 128 columns run the SMALL kernel shape
+static TcLayout tc_layout(const captra_mlp_desc &d, bool f16) {
+    const TcLayout S = tc_layout_v(d, f16, true);
+    return S.supported ? S : tc_layout_v(d, f16, false);
 }
 
 int64_t tc_pack_bytes(const captra_mlp_desc *d, bool f16) {
@@ -729,7 +762,7 @@ int64_t tc_pack_bytes(const captra_mlp_desc *d, bool f16) {
 
 int tc_pack(const captra_mlp_desc *d, void *packed, bool f16, cudaStream_t stream) {
     const TcLayout L = tc_layout(*d, f16);
-    const int KC = tc_kc(f16);
+    const int KC = tc_kc(f16, L.small), TC_NCHUNK = L.nchunk;
     CAPTRA_REQUIRE(L.supported, "mlp_pack(tc): layer widths not supported by the tcgen05 path");
     int cin = d->cin;      // true input width of layer l (the packed K is zero padded to L.kpad[l])
     for (int l = 0; l < d->nlayers; ++l) {
@@ -742,8 +775,8 @@ int tc_pack(const captra_mlp_desc *d, void *packed, bool f16, cudaStream_t strea
             float *wp = base + L.off_w[l] + (size_t)y * (L.kpad[l] / KC) * 2 * TC_NCHUNK * 256 * 4;
             tc_scale_kernel<<<1, 256, 0, stream>>>(cin, cout_y, npad_y, f16 ? 1 : 0, w_y, d->bias[l] ? d->bias[l] + y * 256 : nullptr, bp);
             CAPTRA_CHECK_LAUNCH("mlp_pack(tc scale)");
-            if (f16) pack_tc_kernel<true><<<64, 256, 0, stream>>>(cin, cout_y, L.kpad[l], npad_y, w_y, bp, wp);
-            else pack_tc_kernel<false><<<64, 256, 0, stream>>>(cin, cout_y, L.kpad[l], npad_y, w_y, bp, wp);
+            if (f16) pack_tc_kernel<true><<<64, 256, 0, stream>>>(cin, cout_y, L.kpad[l], npad_y, TC_NCHUNK, w_y, bp, wp);
+            else pack_tc_kernel<false><<<64, 256, 0, stream>>>(cin, cout_y, L.kpad[l], npad_y, TC_NCHUNK, w_y, bp, wp);
             CAPTRA_CHECK_LAUNCH("mlp_pack(tc)");
         }
         cin = d->cout[l];
@@ -753,7 +786,7 @@ int tc_pack(const captra_mlp_desc *d, void *packed, bool f16, cudaStream_t strea
 
 static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool f16, size_t *smem) {
     const TcLayout L = tc_layout(*d, f16);
-    a.f16 = f16 ? 1 : 0;
+    a.f16 = f16 ? 1 : 0; a.small = L.small ? 1 : 0;
     CAPTRA_REQUIRE(L.supported, "mlp(tc): layer widths not supported by the tcgen05 path");
     a.nlayers = d->nlayers; a.relu_last = d->relu_last; a.cout_last = d->cout[d->nlayers - 1];
     for (int l = 0; l < d->nlayers; ++l) {
@@ -765,7 +798,7 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool
     a.region_cols = L.region_cols; a.tmem_cols = L.tmem_cols; a.nst_log2 = L.nstages == 4 ? 2 : 1;
     a.nsplit = L.nsplit; a.last_npad = L.last_npad; a.cout_total = d->cout[d->nlayers - 1];
     {
-        const int kc = tc_kc(f16), kmma = f16 ? 16 : 8;
+        const int kc = tc_kc(f16, L.small), kmma = f16 ? 16 : 8;
         a.cin0 = d->cin;
         const int rem = d->cin - (L.kpad[0] / kc - 1) * kc;     // channels in layer 0's last slab
         a.klast0 = ceil_div(rem, kmma);
@@ -775,20 +808,22 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool
     return CAPTRA_OK;
 }
 
-template <int MODE, bool F16>
+template <int MODE, bool F16, bool SMALL>
 static int tc_launch_t(TcArgs &a, size_t smem, cudaStream_t stream) {
-    auto kern = mlp_tc_kernel<MODE, F16>;
+    auto kern = mlp_tc_kernel<MODE, F16, SMALL>;
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
-    const int64_t slots = (int64_t)max(1, sm_count() / a.nsplit);     // one CTA per SM
+    const int64_t slots = (int64_t)max(1, sm_count() / a.nsplit) * (SMALL ? 2 : 1);
     const int gx = (int)(a.ntiles < slots ? a.ntiles : slots);
-    kern<<<dim3(gx, a.nsplit), TC_THREADS, smem, stream>>>(a);
+    kern<<<dim3(gx, a.nsplit), SMALL ? 192 : 320, smem, stream>>>(a);
     CAPTRA_CHECK_LAUNCH("mlp_tc");
     return CAPTRA_OK;
 }
 template <int MODE>
 static int tc_launch(TcArgs &a, size_t smem, cudaStream_t stream) {
-    return a.f16 ? tc_launch_t<MODE, true>(a, smem, stream) : tc_launch_t<MODE, false>(a, smem, stream);
+    if (a.small) return a.f16 ? tc_launch_t<MODE, true, true>(a, smem, stream) : tc_launch_t<MODE, false, true>(a, smem, stream);
+    return a.f16 ? tc_launch_t<MODE, true, false>(a, smem, stream) : tc_launch_t<MODE, false, false>(a, smem, stream);
 }
 
 int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const float *new_xyz,
@@ -913,6 +948,17 @@ int tc_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, cons
     return tc_point_mlp_ex(rows, x, ldx, cin, nullptr, 0, 0, 0, d, packed, y, ldy, col_off, 0, f16, stream, in_scale, in_shift, rows_per_cloud);
 }
 }  // namespace captra
+
+extern "C" int captra_f16_overflow_flag(int reset) {
+    int v = 0;
+    CAPTRA_CUDA(cudaDeviceSynchronize());
+    CAPTRA_CUDA(cudaMemcpyFromSymbol(&v, g_f16_overflow, sizeof(int)));
+    if (reset) {
+        int zero = 0;
+        CAPTRA_CUDA(cudaMemcpyToSymbol(g_f16_overflow, &zero, sizeof(int)));
+    }
+    return v ? -1 : 0;
+}
 
 extern "C" int captra_debug_tc_timestamps(long long *out_host, int max_pairs) {
     int n = 0;

@@ -13,10 +13,20 @@ import torch
 from . import _lib
 
 MAX_LAYERS = 4
-# 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel (default), 2 = tcgen05 fp16x3 kernel
-# (same split arithmetic on fp16 operands: half the operand bytes, K=16 per MMA; activations
-# saturate at 65504).  CAPTRA_MLP_IMPL overrides.
-DEFAULT_IMPL = int(os.environ.get("CAPTRA_MLP_IMPL", "1"))
+# 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 3xTF32 kernel, 2 = tcgen05 fp16x3 kernel (default: the
+# same hi/lo split arithmetic on fp16 operands -- 22 mantissa bits, half the operand bytes, K=16 per
+# MMA; operands saturate at 65504 and f16_overflowed() reports if that ever happened).
+# CAPTRA_MLP_IMPL overrides.
+DEFAULT_IMPL = int(os.environ.get("CAPTRA_MLP_IMPL", "2"))
+
+
+def f16_overflowed(reset=True):
+    """True if an fp16x3 kernel met an operand >= 65504 since the last reset (device sync).  Such a
+    result is not fp32-accurate: re-run with CAPTRA_MLP_IMPL=1 (3xTF32, full exponent range)."""
+    rc = _lib.load().captra_f16_overflow_flag(1 if reset else 0)
+    if rc > 0:
+        raise _lib.CaptraError("f16_overflow_flag: " + _lib.load().captra_last_error().decode())
+    return rc < 0
 
 
 class MlpDesc(ctypes.Structure):

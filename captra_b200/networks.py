@@ -27,7 +27,8 @@ def normalize_vector(v):
     """rotations.py:300-312."""
     mag = torch.norm(v, p=2, dim=1, keepdim=True)
     valid = (mag > 1e-8).float()
-    backup = torch.tensor([1.0, 0.0, 0.0], device=v.device).view(1, 3).expand_as(v)
+    backup = torch.zeros_like(v)          # (1, 0, 0), built on the device (CUDA-graph capturable)
+    backup[:, 0] = 1.0
     return (v / torch.clamp(mag, min=1e-8)) * valid + backup * (1 - valid)
 
 
@@ -223,9 +224,13 @@ class RotationRegressionBackbone(nn.Module):
             mask = (labels == p).float().unsqueeze(1)                               # [B, 1, N]
             cnt = mask.sum(-1)
             mean = (raw * mask).sum(-1) / torch.clamp_min(cnt, 1.0)
-            default = torch.tensor((0., 1., 0.)) if self.sym else torch.eye(3).reshape(-1)
+            if self.sym:                   # defaults built on the device (CUDA-graph capturable)
+                default = torch.zeros(3, device=raw.device)
+                default[1:2] = 1.0         # slice, not an int index: the latter copies a CPU scalar (not capturable)
+            else:
+                default = torch.eye(3, device=raw.device).reshape(-1)
             valid = (cnt > 0).float()
-            out.append(valid * mean + (1.0 - valid) * default.to(raw.device).reshape(1, -1))
+            out.append(valid * mean + (1.0 - valid) * default.reshape(1, -1))
         return torch.stack(out, dim=1)
 
 

@@ -164,6 +164,11 @@ int captra_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const
                      const void *packed, float *y, int64_t ldy, int col_off, int group, int impl,
                      captra_stream_t stream);
 
+/* impl 2 (fp16x3) keeps fp32-class accuracy only while |activation| < 65504; the kernels record any
+ * larger value.  Synchronises the device; returns 0 (clean), -1 (an operand saturated: re-run the
+ * model with impl 1) or a positive error code.  reset != 0 clears the record. */
+int captra_f16_overflow_flag(int reset);
+
 /* GroupNorm folded into the consumer layer (RotationRegressor heads, blocks.py:146-193: conv1d ->
  * GroupNorm(C/2 groups) -> ReLU).  captra_group_norm_affine turns the statistics of a pre-norm
  * activation y [clouds*npts, C] (point-major) into per-(cloud, channel) scale/shift; the next

@@ -112,3 +112,30 @@ def test_track_multi_frame_stays_finite(cuda):
     for _ in range(3):
         pose = trk.step(pts, mean, pose)
     assert all(torch.isfinite(v).all() for v in pose.values())
+
+
+@pytest.mark.parametrize("category", ["laptop", "bottle"])
+def test_graphed_step_equals_eager_and_no_overflow(category, cuda):
+    from captra_b200 import mlp, track
+    cfg = track.make_cfg(category)
+    trk = track.Tracker(cfg, seed=1).to(cuda).eval()
+    mlp.f16_overflowed(reset=True)
+    b = track.synthetic_track_batch(4, category, seed=2)
+    pts, mean = torch.from_numpy(b["points"]).to(cuda), torch.from_numpy(b["points_mean"]).to(cuda)
+    pose = {k: torch.from_numpy(v).to(cuda) for k, v in b["pose"].items()}
+    eager = {k: v.clone() for k, v in trk.step(pts, mean, pose).items()}
+    gs = track.GraphedStep(trk, pts, mean, pose)
+    assert gs.launches_per_replay > 20
+    for _ in range(2):
+        got = gs(pts, mean, pose)
+    for k in eager:
+        assert torch.equal(got[k], eager[k]), k
+    # a different input through the same graph
+    b2 = track.synthetic_track_batch(4, category, seed=3)
+    pts2, mean2 = torch.from_numpy(b2["points"]).to(cuda), torch.from_numpy(b2["points_mean"]).to(cuda)
+    pose2 = {k: torch.from_numpy(v).to(cuda) for k, v in b2["pose"].items()}
+    want2 = {k: v.clone() for k, v in trk.step(pts2, mean2, pose2).items()}
+    got2 = gs(pts2, mean2, pose2)
+    for k in want2:
+        assert torch.equal(got2[k], want2[k]), k
+    assert not mlp.f16_overflowed()
