@@ -54,19 +54,23 @@ class PointNet2Msg(nn.Module):
             return PackedMLP([w for w, _ in wb], [b for _, b in wb], relu_last=True)
         return self._cache.get(self, build)
 
-    def forward_pm(self, input):
-        """input [B,3,N] -> feat [B,N,out_dim] (point-major), fused inference path."""
+    def forward_pm(self, input, geom=None):
+        """input [B,3,N] -> feat [B,N,out_dim] (point-major), fused inference path.  `geom`: an
+        (initially empty) dict that receives every coordinate-only result (FPS picks, ball-query
+        index lists, 3-NN indices and weights); passing the same dict to a second backbone that is
+        evaluated on the *same* input coordinates reuses them (bit-identical, they depend on xyz only)."""
+        g = (lambda k: geom.setdefault(k, {})) if geom is not None else (lambda k: None)
         l0_xyz = input.transpose(1, 2).contiguous()                       # [B,N,3]
         l0_feats = l0_xyz if self.use_xyz_feat else None                   # backbones.py:57-60
-        l1_xyz, l1_feats = self.sa1.forward_pm(l0_xyz, l0_feats)
-        l2_xyz, l2_feats = self.sa2.forward_pm(l1_xyz, l1_feats)
+        l1_xyz, l1_feats = self.sa1.forward_pm(l0_xyz, l0_feats, geom=g("sa1"))
+        l2_xyz, l2_feats = self.sa2.forward_pm(l1_xyz, l1_feats, geom=g("sa2"))
         l3_feats = self.sa3.forward_pm(l2_xyz, l2_feats)                   # [B,1024]
         B = input.shape[0]
         l3_xyz = torch.zeros(B, 1, 3, device=input.device)
         l2_feats = self.fp3.forward_pm(l2_xyz, l3_xyz, l2_feats, l3_feats.view(B, 1, -1))
-        l1_feats = self.fp2.forward_pm(l1_xyz, l2_xyz, l1_feats, l2_feats)
+        l1_feats = self.fp2.forward_pm(l1_xyz, l2_xyz, l1_feats, l2_feats, geom=g("fp2"))
         skip = torch.cat([l0_xyz, l0_xyz], dim=-1) if self.use_xyz_feat else l0_xyz   # backbones.py:67
-        return self.fp1.forward_pm(l0_xyz, l1_xyz, skip, l1_feats, mlp=self._fp1_head())
+        return self.fp1.forward_pm(l0_xyz, l1_xyz, skip, l1_feats, mlp=self._fp1_head(), geom=g("fp1"))
 
     def forward(self, input):  # [B,3,N]
         if not _needs_autograd(self, input):

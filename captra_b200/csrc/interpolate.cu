@@ -282,12 +282,15 @@ extern "C" int captra_three_nn_interpolate(int b, int c, int n, int m, const flo
                                            captra_stream_t stream) {
     CAPTRA_REQUIRE(b >= 0 && c >= 0 && m >= 1 && n >= 0, "three_nn_interpolate: bad size");
     if (b == 0 || n == 0) return CAPTRA_OK;
-    CAPTRA_REQUIRE(unknown && known && idx && weight, "three_nn_interpolate: idx/weight scratch required");
+    CAPTRA_REQUIRE(idx && weight, "three_nn_interpolate: idx/weight buffers required");
     CAPTRA_REQUIRE(b <= 65535, "three_nn_interpolate: batch exceeds grid limit");
     cudaStream_t s = as_stream(stream);
-    dim3 g1(ceil_div(n, NN_THREADS), b);
-    three_nn_weights_kernel<<<g1, NN_THREADS, 0, s>>>(n, m, unknown, known, dist, idx, weight);
-    CAPTRA_CHECK_LAUNCH("three_nn_weights");
+    if (unknown) {   // unknown == NULL: idx/weight are inputs (geometry shared between two networks)
+        CAPTRA_REQUIRE(known, "three_nn_interpolate: null known");
+        dim3 g1(ceil_div(n, NN_THREADS), b);
+        three_nn_weights_kernel<<<g1, NN_THREADS, 0, s>>>(n, m, unknown, known, dist, idx, weight);
+        CAPTRA_CHECK_LAUNCH("three_nn_weights");
+    }
     if (c == 0 || !out) return CAPTRA_OK;
     CAPTRA_REQUIRE(points, "three_nn_interpolate: null points");
     if (point_major) {

@@ -36,18 +36,25 @@ def ball_query_multi(radii, nsamples, xyz, new_xyz):
     return outs
 
 
-def three_nn_interpolate_pm(unknown, known, feats_pm, out=None, col_off=0):
+def three_nn_interpolate_pm(unknown, known, feats_pm, out=None, col_off=0, nn=None, return_nn=False):
     """unknown [B,n,3], known [B,m,3], feats_pm [B,m,C] -> out [B,n,C] (or into out[..., col_off:]);
-    3-NN + inverse-distance weights + interpolation (pointnet_utils.py:284-289)."""
+    3-NN + inverse-distance weights + interpolation (pointnet_utils.py:284-289).  `nn` = (idx, weight)
+    from an earlier call on the same coordinates skips the search."""
     B, n, _ = unknown.shape
     m, C = known.shape[1], feats_pm.shape[2]
     dev = unknown.device
-    idx = torch.empty(B, n, 3, dtype=_i32, device=dev)
-    w = torch.empty(B, n, 3, dtype=_f32, device=dev)
+    if nn is None:
+        idx = torch.empty(B, n, 3, dtype=_i32, device=dev)
+        w = torch.empty(B, n, 3, dtype=_f32, device=dev)
+        uptr = _lib.ptr(unknown, _f32, "unknown")
+    else:
+        idx, w = nn
+        uptr = None
     if out is None:
         out = torch.empty(B, n, C, dtype=_f32, device=dev)
-    _lib.call("three_nn_interpolate[B=%d,n=%d,m=%d,C=%d]" % (B, n, m, C), _lib.load().captra_three_nn_interpolate,
-              B, C, n, m, _lib.ptr(unknown, _f32, "unknown"), _lib.ptr(known, _f32, "known"),
+    _lib.call("three_nn_interpolate[B=%d,n=%d,m=%d,C=%d%s]" % (B, n, m, C, ",reuse" if nn is not None else ""),
+              _lib.load().captra_three_nn_interpolate,
+              B, C, n, m, uptr, _lib.ptr(known, _f32, "known"),
         _lib.ptr(feats_pm, _f32, "feats"), _lib.ptr(out, _f32, "out"), None, idx.data_ptr(), w.data_ptr(),
         1, out.shape[-1], col_off, _lib.stream_ptr(dev), device=dev)
-    return out
+    return (out, (idx, w)) if return_nn else out

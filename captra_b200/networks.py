@@ -180,7 +180,7 @@ class CoordNet(nn.Module):
         assert 'gt_part' not in input, "training-time pose branch (networks.py:54-108) is not mirrored"
         cam = canonicalize(input['points'], input['points_mean'], input['canon_pose'])
         if not _needs_autograd(self, cam):
-            feat = self.backbone.forward_pm(cam)                    # [B,N,C] point-major
+            feat = self.backbone.forward_pm(cam, geom=input.get('geom'))   # [B,N,C] point-major
             B, N, C = feat.shape
             seg_mlp, nocs_mlp = self._packed_heads()
             seg = F.softmax(seg_mlp.rows(feat.reshape(B * N, C)).view(B, N, -1), dim=-1).transpose(1, 2)
@@ -202,14 +202,14 @@ class RotationRegressionBackbone(nn.Module):
         self.sym = cfg['obj_sym']
         self.pose_pred = RotationRegressor(cfg['network']['backbone_out_dim'], self.num_parts, symmetric=self.sym)
 
-    def forward_diag(self, cam, labels, batch_size):
+    def forward_diag(self, cam, labels, batch_size, geom=None):
         """cam [B*P,3,N] (copy p canonicalised by part p), labels [B,N] -> rtvec [B,P,D]: head p on
         copy p, masked mean over part p's points (networks.py:127-139 restricted to the diagonal
         that networks.py:200-203 keeps)."""
         P = self.num_parts
         fused = _mlp.DEFAULT_IMPL in (1, 2) and not _needs_autograd(self, cam)
         if fused:
-            feat_pm = self.encoder.forward_pm(cam)                 # [B*P, N, C] point-major
+            feat_pm = self.encoder.forward_pm(cam, geom=geom)      # [B*P, N, C] point-major
             feat_pm = feat_pm.reshape(batch_size, P, feat_pm.shape[1], feat_pm.shape[2])
         else:
             feat = self.encoder(cam)                               # [B*P, C, N]
@@ -262,7 +262,9 @@ class PartCanonNet(nn.Module):
         cam_rep = cam.unsqueeze(1).expand(-1, P, -1, -1).reshape((-1,) + cam.shape[-2:])
         mean_rep = points_mean.unsqueeze(1).expand(-1, P, -1, -1).reshape((-1,) + points_mean.shape[-2:])
         cam_rep = canonicalize(cam_rep, mean_rep, canon_pose)
-        rtvec = self.regress_net.forward_diag(cam_rep, labels, B)              # [B,P,D]
+        # a rigid object (P == 1) is canonicalised by the same pose in both networks: share the geometry
+        geom = input.get('geom') if P == 1 and 'canon_pose' not in input else None
+        rtvec = self.regress_net.forward_diag(cam_rep, labels, B, geom=geom)    # [B,P,D]
         delta_rot = convert_pred_rtvec_to_matrix(rtvec, self.sym)                # [B,P,3,3]
         rotation = torch.matmul(part_pose['rotation'], delta_rot)                # part_dof_utils.py:124-128
         pred_npcs = input['pred_nocs'].reshape(B, P, 3, -1)

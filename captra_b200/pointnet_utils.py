@@ -150,14 +150,21 @@ class PointNetSetAbstractionMsg(nn.Module):
             return out
         return self._cache.get(self, build)
 
-    def forward_pm(self, xyz_pm, feats_pm):
+    def forward_pm(self, xyz_pm, feats_pm, geom=None):
         """Fused inference path on point-major tensors: xyz [B,N,3], feats [B,N,D] or None ->
-        (new_xyz [B,S,3], new_feats [B,S,sum(cout)])."""
+        (new_xyz [B,S,3], new_feats [B,S,sum(cout)]).  `geom` (a dict) carries the sampling and
+        grouping indices: filled on the first call, reused when another network runs on the very
+        same coordinates (CoordNet / RotationNet of a rigid object)."""
         assert not self.knn, "knn grouping is dead in the reference (knn=False everywhere)"
         if feats_pm is not None and feats_pm.shape[-1] == 0:
             feats_pm = None
-        _, new_xyz = fused_ops.fps_gather(xyz_pm, self.npoint)
-        idxs = fused_ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_pm, new_xyz)
+        if geom is not None and "new_xyz" in geom:
+            new_xyz, idxs = geom["new_xyz"], geom["idxs"]
+        else:
+            _, new_xyz = fused_ops.fps_gather(xyz_pm, self.npoint)
+            idxs = fused_ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_pm, new_xyz)
+            if geom is not None:
+                geom["new_xyz"], geom["idxs"] = new_xyz, idxs
         out = torch.empty(xyz_pm.shape[0], self.npoint, self.out_channel, dtype=torch.float32, device=xyz_pm.device)
         off = 0
         for mlp, idx in zip(self._packed(), idxs):
@@ -216,9 +223,10 @@ class PointNetFeaturePropagation(nn.Module):
             return PackedMLP([w for w, _ in wb], [b for _, b in wb], relu_last=True)
         return self._cache.get(self, build)
 
-    def forward_pm(self, xyz1_pm, xyz2_pm, points1_pm, points2_pm, mlp=None):
+    def forward_pm(self, xyz1_pm, xyz2_pm, points1_pm, points2_pm, mlp=None, geom=None):
         """Fused inference path: xyz1 [B,N,3], xyz2 [B,S,3], points1 [B,N,D1] or None,
-        points2 [B,S,D2] -> [B,N,cout].  `mlp` lets the caller append layers (backbones.py:68)."""
+        points2 [B,S,D2] -> [B,N,cout].  `mlp` lets the caller append layers (backbones.py:68);
+        `geom` caches the 3-NN indices/weights for a second network on the same coordinates."""
         B, N, _ = xyz1_pm.shape
         S = xyz2_pm.shape[1]
         mlp = mlp or self._packed()
@@ -226,7 +234,12 @@ class PointNetFeaturePropagation(nn.Module):
         if S == 1:  # pointnet_utils.py:281-282: repeat the single coarse point
             out = mlp.rows(segA, points2_pm.reshape(B, -1), bcast_rows=N)
         else:
-            interp = fused_ops.three_nn_interpolate_pm(xyz1_pm, xyz2_pm, points2_pm)
+            if geom is not None and "nn" in geom:
+                interp = fused_ops.three_nn_interpolate_pm(xyz1_pm, xyz2_pm, points2_pm, nn=geom["nn"])
+            elif geom is not None:
+                interp, geom["nn"] = fused_ops.three_nn_interpolate_pm(xyz1_pm, xyz2_pm, points2_pm, return_nn=True)
+            else:
+                interp = fused_ops.three_nn_interpolate_pm(xyz1_pm, xyz2_pm, points2_pm)
             out = mlp.rows(segA, interp.reshape(B * N, -1))
         return out.view(B, N, -1)
 

@@ -74,12 +74,16 @@ class Tracker(torch.nn.Module):
         """model.py:454-476.  points [B,3,N] (mean-subtracted), points_mean [B,3,1],
         last_pose {'rotation' [B,P,3,3], 'translation' [B,P,3,1], 'scale' [B,P]} -> new pose dict."""
         canon = {k: last_pose[k][:, self.root] for k in ("rotation", "translation", "scale")}
-        pred = self.npcs_net({"points": points, "points_mean": points_mean, "canon_pose": canon})
+        # With one rigid part both networks see the cloud canonicalised by the same pose
+        # (networks.py:38-41 vs :184-187), so FPS picks, ball-query lists and 3-NN weights -- functions
+        # of the coordinates only -- are computed once and shared (bit-identical results).
+        geom = {} if self.num_parts == 1 else None
+        pred = self.npcs_net({"points": points, "points_mean": points_mean, "canon_pose": canon, "geom": geom})
         B = points.shape[0]
         pred_npcs = pred["nocs"].reshape(B, self.num_parts, 3, -1)
         pred_labels = torch.max(pred["seg"], dim=-2)[1]
         out = self.net({"points": points, "points_mean": points_mean, "state": {"part": last_pose},
-                        "pred_labels": pred_labels, "pred_nocs": pred_npcs}, test_mode=True)
+                        "pred_labels": pred_labels, "pred_nocs": pred_npcs, "geom": geom}, test_mode=True)
         return out["part"]
 
 

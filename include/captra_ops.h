@@ -112,7 +112,9 @@ int captra_fps_gather(int b, int n, int m, const float *dataset, float *temp, in
  * outputs; dist (the sqrt'ed distance ThreeNN returns, pointnet2_utils.py:134) may be NULL.
  * point_major == 0: reference layout, points [B,C,m] -> out [B,C,n].
  * point_major == 1: points [B,m,C] -> out row (b*n+i) at out + row*out_row_stride +
- *                   out_col_offset (lets the caller write straight into a concat buffer). */
+ *                   out_col_offset (lets the caller write straight into a concat buffer).
+ * unknown == NULL skips the search: idx and weight are then inputs (the two networks of a rigid
+ * object see the same canonicalised cloud and share one search). */
 int captra_three_nn_interpolate(int b, int c, int n, int m, const float *unknown,
                                 const float *known, const float *points, float *out,
                                 float *dist, int *idx, float *weight, int point_major,
