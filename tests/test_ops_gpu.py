@@ -193,3 +193,29 @@ def test_empty_batch_and_zero_sizes(futils, cuda):
     assert futils.furthest_point_sample(torch.zeros(0, 10, 3, device=cuda), 4).shape == (0, 4)
     out = futils.grouping_operation(torch.zeros(2, 0, 10, device=cuda), torch.zeros(2, 3, 4, dtype=torch.int32, device=cuda))
     assert out.shape == (2, 0, 3, 4)
+
+
+@pytest.mark.parametrize("kind,n,m,radius,k", [
+    ("surface", 16384, 512, 0.05, 64),      # BASELINE cfg5 level 1: sparse balls, sorted-candidate path
+    ("uniform", 12000, 300, 0.08, 32),
+    ("surface", 16384, 256, 0.3, 64),       # dense balls: > 512 candidates -> early-exit scan fallback
+    ("tiled", 10000, 200, 0.06, 48),        # exact duplicates
+    ("surface", 20480, 128, 0.02, 16),      # many empty balls
+])
+def test_ball_query_grid_path_bit_exact(kind, n, m, radius, k, futils, oracle, refcu, cuda):
+    """Large clouds take the binned search (csrc/ball_query.cu); same hits, same order as the scan."""
+    if kind == "surface":
+        pts = np.stack([synthetic.surface_box(n, np.random.default_rng(7 + i))[0] for i in range(2)])
+    elif kind == "uniform":
+        pts = synthetic.batch_uniform(2, n, seed=3)
+    else:
+        pts = synthetic.batch_tiled(2, n, 1234, seed=4)
+    ctr = np.ascontiguousarray(pts[:, ::n // m][:, :m]).copy()
+    ctr[0, 0] += 50.0                      # far outside the bounding box: empty
+    ctr[1, 1] = pts[1].min(0) - 0.9 * radius   # just outside the box corner
+    ctr[0, 2, 0] = np.nan                  # NaN centroid: no hits
+    want = oracle.ball_query(radius, k, pts, ctr)
+    got = futils.ball_query(radius, k, dev(pts, cuda), dev(ctr, cuda))
+    assert np.array_equal(got.cpu().numpy(), want)
+    ref = refcu.ball_query(radius, k, dev(pts, cuda), dev(ctr, cuda))
+    assert np.array_equal(ref.cpu().numpy(), want)
