@@ -143,14 +143,24 @@ static int launch_bq(int b, int n, int m, const BQParams &prm, const float *new_
 // away from the HBM roofline of the op.  Here each cloud is binned into a uniform grid with cell
 // size h >= r(1+1e-5) (so every hit lies in the 27 cells around the centroid), a warp tests only
 // those cells with the SAME exact-order fp32 distance, and the hit indices are sorted ascending in
-// shared memory, which reproduces "the first K hits in index order" bit for bit.  Dense balls
+// a per-warp bitmap and read back in ascending order, which reproduces "the first K hits in index
+// order" bit for bit.  Dense balls
 // (more than BQG_CAP candidates, where the serial scan would exit early anyway) fall back to the
 // early-exit scan inside the same warp.
 // ------------------------------------------------------------------------------------------------
 constexpr int BQG_DIM = 32;                    // max cells per axis
 constexpr int BQG_MAXCELL = BQG_DIM * BQG_DIM * BQG_DIM;
-constexpr int BQG_CAP = 512;                   // candidate capacity per centroid (ints in smem)
-constexpr int BQG_QWARPS = 4;                  // centroids (warps) per query CTA
+constexpr int BQG_CAP = 512;                   // more hits than this: the early-exit scan is cheaper
+constexpr int BQG_MAX_SMEM = 200 << 10;        // bitmap budget of the one-warp-per-CTA variant
+
+static inline int bq_grid_wpl_log2(int n) {    // bitmap words per lane (power of two) covering n bits
+    int l = 0;
+    while ((1024ll << l) < n) ++l;
+    return l;
+}
+static inline bool bq_grid_fits(int n, int nsample) {
+    return sizeof(int) * (32 * ((size_t)(1 << bq_grid_wpl_log2(n)) | 1) + (size_t)nsample) <= (size_t)BQG_MAX_SMEM;
+}
 
 struct BQGrid {          // per cloud, written by the build kernel
     float minx, miny, minz, inv_h;
@@ -259,39 +269,32 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz, BQGrid 
     }
 }
 
-// warp-wide bitonic sort of cand[0..np) (np a power of two <= BQG_CAP) ascending
-__device__ __forceinline__ void warp_bitonic_sort(int *cand, int np, int lane) {
-    for (int k = 2; k <= np; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = lane; i < np; i += 32) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const int a = cand[i], c = cand[l];
-                    const bool up = (i & k) == 0;
-                    if ((a > c) == up) { cand[i] = c; cand[l] = a; }
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-__global__ void __launch_bounds__(BQG_QWARPS * 32)
-bq_grid_query_kernel(int n, int m, float radius2, int nsample, const float *__restrict__ new_xyz,
+// One warp per centroid.  Hits are recorded as bits of a per-warp index bitmap in shared memory, so
+// reading the bitmap back in word order yields them in ascending index order -- no sort.  Lane l owns
+// the wpl consecutive words [l*wpl, (l+1)*wpl), stored at an odd stride so the per-lane walks are
+// bank-conflict free.
+template <int QW>
+__global__ void __launch_bounds__(QW * 32)
+bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, const float *__restrict__ new_xyz,
                      const float *__restrict__ xyz, const BQGrid *__restrict__ grids,
                      const int *__restrict__ cell_start, const float4 *__restrict__ sorted, int *__restrict__ idx) {
-    __shared__ int cand_s[BQG_QWARPS][BQG_CAP];
+    extern __shared__ unsigned bq_smem[];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = blockIdx.x * BQG_QWARPS + warp;
+    const int ci = blockIdx.x * QW + warp;
     if (ci >= m) return;
+    const int wpl = 1 << wpl_log2, stride = wpl | 1;
+    unsigned *bm = bq_smem + (size_t)warp * (32 * stride + nsample);
+    int *stage = reinterpret_cast<int *>(bm + 32 * stride);
+    unsigned *mine = bm + lane * stride;
+    for (int j = 0; j < wpl; ++j) mine[j] = 0u;
     const unsigned lt = lanemask_lt();
-    int *cand = cand_s[warp];
     const BQGrid g = grids[b];
     const float *cp = new_xyz + ((size_t)b * m + ci) * 3;
     const float cx = __ldg(cp), cy = __ldg(cp + 1), cz = __ldg(cp + 2);
     int *row = idx + ((size_t)b * m + ci) * nsample;
     const int *cs = cell_start + (size_t)b * (BQG_MAXCELL + 1);
     const float4 *pts = sorted + (size_t)b * n;
+    __syncwarp();
 
     int cnt = 0;
     bool overflow = false;
@@ -299,30 +302,55 @@ bq_grid_query_kernel(int n, int m, float radius2, int nsample, const float *__re
         // the centroid's own cell, unclamped: a centroid outside the box still sees the right neighbours
         const int ix = (int)floorf((cx - g.minx) * g.inv_h), iy = (int)floorf((cy - g.miny) * g.inv_h),
                   iz = (int)floorf((cz - g.minz) * g.inv_h);
-        for (int zz = max(iz - 1, 0); zz <= min(iz + 1, g.dz - 1) && !overflow; ++zz)
-            for (int yy = max(iy - 1, 0); yy <= min(iy + 1, g.dy - 1) && !overflow; ++yy) {
-                const int x0 = max(ix - 1, 0), x1 = min(ix + 1, g.dx - 1);
-                if (x0 > x1) continue;
-                // cells x0..x1 of one (y,z) row are contiguous in the sorted array
-                const int beg = cs[(zz * g.dy + yy) * g.dx + x0], end = cs[(zz * g.dy + yy) * g.dx + x1 + 1];
-                for (int base = beg; base < end; base += 32) {
-                    const int k = base + lane;
-                    bool hit = false;
-                    int pidx = 0;
-                    if (k < end) {
-                        const float4 p = __ldg(pts + k);
-                        hit = sqdist_ref(cx, cy, cz, p.x, p.y, p.z) < radius2;
-                        pidx = __float_as_int(p.w);
-                    }
-                    const unsigned bal = __ballot_sync(kFull, hit);
-                    if (bal) {
-                        const int pos = cnt + __popc(bal & lt);
-                        if (hit && pos < BQG_CAP) cand[pos] = pidx;
-                        cnt += __popc(bal);
-                        if (cnt > BQG_CAP) { overflow = true; break; }
-                    }
-                }
+        // Cells x0..x1 of one (y,z) row are contiguous in the binned array, so the 27 cells are nine
+        // segments.  Lane r < 9 fetches segment r's bounds (one round trip for all nine), and the
+        // candidates are then walked as one flat list, 32 per step, with the next step's points in flight.
+        int seg_beg = 0, seg_len = 0;
+        if (lane < 9) {
+            const int zz = iz - 1 + lane / 3, yy = iy - 1 + lane % 3;
+            const int x0 = max(ix - 1, 0), x1 = min(ix + 1, g.dx - 1);
+            if (zz >= 0 && zz < g.dz && yy >= 0 && yy < g.dy && x0 <= x1) {
+                const int rowc = (zz * g.dy + yy) * g.dx;
+                seg_beg = __ldg(cs + rowc + x0);
+                seg_len = __ldg(cs + rowc + x1 + 1) - seg_beg;
             }
+        }
+        int incl = seg_len;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(kFull, incl, 8);
+        // flat position f lies in segment r iff se[r-1] <= f < se[r]; its binned slot is f + dl[r]
+        const int delta = seg_beg - (incl - seg_len);
+        int dl[9], se[8];
+#pragma unroll
+        for (int r = 0; r < 9; ++r) dl[r] = __shfl_sync(kFull, delta, r);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) se[r] = __shfl_sync(kFull, incl, r);
+        auto fetch = [&](int f, float4 &p) -> bool {
+            if (f >= total) return false;
+            int d = dl[0];
+#pragma unroll
+            for (int r = 1; r < 9; ++r) d = f >= se[r - 1] ? dl[r] : d;
+            p = __ldg(pts + f + d);
+            return true;
+        };
+        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool have_next = fetch(lane, p_next);
+        for (int t = 0; t < total; t += 32) {
+            const float4 p = p_next;
+            const bool have = have_next;
+            have_next = fetch(t + 32 + lane, p_next);
+            const bool hit = have && sqdist_ref(cx, cy, cz, p.x, p.y, p.z) < radius2;
+            if (hit) {
+                const int k = __float_as_int(p.w), w = k >> 5;
+                atomicOr(bm + (w >> wpl_log2) * stride + (w & (wpl - 1)), 1u << (k & 31));
+            }
+            cnt += __popc(__ballot_sync(kFull, hit));
+            if (cnt > BQG_CAP) { overflow = true; break; }
+        }
     }
     if (overflow) {
         // dense ball: the reference's serial scan exits early here; do exactly that (warp-wide)
@@ -345,13 +373,27 @@ bq_grid_query_kernel(int n, int m, float radius2, int nsample, const float *__re
     }
     if (cnt == 0) return;                      // empty ball: the caller's zeros stay
     __syncwarp();
-    int np = 1;
-    while (np < cnt) np <<= 1;
-    for (int i = cnt + lane; i < np; i += 32) cand[i] = 0x7fffffff;
+    // ---- read the bitmap back in index order: per-lane popcount, warp prefix, ordered emission
+    int c = 0;
+    for (int j = 0; j < wpl; ++j) c += __popc(mine[j]);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int pos = incl - c;
+    for (int j = 0; j < wpl && pos < nsample; ++j) {
+        unsigned w = mine[j];
+        const int base = (lane * wpl + j) << 5;
+        while (w && pos < nsample) {
+            stage[pos++] = base + __ffs(w) - 1;
+            w &= w - 1;
+        }
+    }
     __syncwarp();
-    warp_bitonic_sort(cand, np, lane);
-    const int first = cand[0];
-    for (int l = lane; l < nsample; l += 32) row[l] = l < cnt ? cand[l] : first;
+    const int keep = min(cnt, nsample), first = stage[0];
+    for (int l = lane; l < nsample; l += 32) row[l] = l < keep ? stage[l] : first;
 }
 
 static int launch_bq_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
@@ -362,6 +404,18 @@ static int launch_bq_grid(int b, int n, int m, float radius, int nsample, const 
     const size_t sz_s = sizeof(float4) * (size_t)b * n;
     const size_t off_c = (sz_g + 255) & ~(size_t)255, off_s = (off_c + sz_c + 255) & ~(size_t)255;
     uint8_t *ws = nullptr;
+    static bool pool_done = false;
+    if (!pool_done) {
+        // keep freed scratch in the stream-ordered pool across synchronisation points (default threshold 0
+        // hands it back to the driver at every sync, and the next frame pays a fresh allocation)
+        int dev = 0;
+        cudaMemPool_t pool;
+        CAPTRA_CUDA(cudaGetDevice(&dev));
+        CAPTRA_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long thr = ~0ull;
+        CAPTRA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        pool_done = true;
+    }
     CAPTRA_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), off_s + sz_s, stream));
     BQGrid *grids = reinterpret_cast<BQGrid *>(ws);
     int *cell_start = reinterpret_cast<int *>(ws + off_c);
@@ -370,12 +424,20 @@ static int launch_bq_grid(int b, int n, int m, float radius, int nsample, const 
     static bool attr_done = false;
     if (!attr_done) {
         CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_query_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10));
+        CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_query_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQG_MAX_SMEM));
         attr_done = true;
     }
     bq_grid_build_kernel<<<b, 1024, smem, stream>>>(n, radius, xyz, grids, cell_start, sorted);
     CAPTRA_CHECK_LAUNCH("ball_query(grid build)");
-    bq_grid_query_kernel<<<dim3(ceil_div(m, BQG_QWARPS), b), BQG_QWARPS * 32, 0, stream>>>(
-        n, m, radius * radius, nsample, new_xyz, xyz, grids, cell_start, sorted, idx);
+    const int wpl_log2 = bq_grid_wpl_log2(n);
+    const size_t per_warp = sizeof(int) * (32 * ((1 << wpl_log2) | 1) + (size_t)nsample);
+    if (4 * per_warp <= (64u << 10))
+        bq_grid_query_kernel<4><<<dim3(ceil_div(m, 4), b), 128, 4 * per_warp, stream>>>(
+            n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids, cell_start, sorted, idx);
+    else
+        bq_grid_query_kernel<1><<<dim3(m, b), 32, per_warp, stream>>>(
+            n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids, cell_start, sorted, idx);
     CAPTRA_CHECK_LAUNCH("ball_query(grid query)");
     CAPTRA_CUDA(cudaFreeAsync(ws, stream));
     return CAPTRA_OK;
@@ -405,9 +467,12 @@ extern "C" int captra_ball_query_multi(int b, int n, int m, int nradii, const fl
         CAPTRA_REQUIRE(prm.nsample[r] >= 0 && (prm.nsample[r] == 0 || prm.idx[r]), "ball_query: bad nsample/idx for radius %d", rr);
     }
     cudaStream_t s = as_stream(stream);
-    // large clouds, one radius: binned search (same hits, same order); CAPTRA_BQ_GRID=0 forces the scan
-    static const int grid_min_n = [] { const char *e = getenv("CAPTRA_BQ_GRID_MIN_N"); return e ? atoi(e) : 8192; }();
-    if (nradii == 1 && n >= grid_min_n && prm.nsample[0] > 0 && radii_host[0] > 0.f && isfinite(radii_host[0]))
+    // larger clouds, one radius: binned search (same hits, same order).  Measured crossover against the
+    // scan on B200 is between N = 1024 and 4096 (profiles/r01_stress_cfg5_*.jsonl); a huge
+    // CAPTRA_BQ_GRID_MIN_N forces the scan.
+    static const int grid_min_n = [] { const char *e = getenv("CAPTRA_BQ_GRID_MIN_N"); return e ? atoi(e) : 2048; }();
+    if (nradii == 1 && n >= grid_min_n && prm.nsample[0] > 0 && radii_host[0] > 0.f && isfinite(radii_host[0]) &&
+        bq_grid_fits(n, prm.nsample[0]))
         return launch_bq_grid(b, n, m, radii_host[0], prm.nsample[0], new_xyz, xyz, prm.idx[0], s);
     switch (nradii) {
         case 1: return launch_bq<1>(b, n, m, prm, new_xyz, xyz, s);

@@ -7,6 +7,8 @@
 // drops by the channel-block factor and every store is a 16-byte streaming store.  The source
 // rows points[b,c,:] (N floats) stay L1/L2 resident.  All offsets are 64-bit (the reference's
 // int offsets overflow at B*C*M*K >= 2^31).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace captra {
@@ -43,6 +45,51 @@ gather_rows_kernel(int c, int n, int64_t L, const float *__restrict__ points,
     }
 }
 
+// Shared-memory variant for the big calls.  With the rows in L1 the kernel above is bound by the
+// load pipe (four divergent 4-byte loads per 16-byte store, ~12 cycles per warp-load measured on
+// cfg5), not by HBM.  Here a CTA copies CB source rows (CB*n floats) into shared memory once and
+// serves every gather from there -- a divergent LDS costs ~3.5 cycles (bank conflicts of 32 random
+// lanes) -- so the streaming stores become the limit.  blockIdx.x splits the L slots of one
+// (cloud, channel block) into chunks when there are too few CTAs otherwise.
+constexpr int GS_THREADS = 512;
+
+template <bool VEC4>
+__global__ void __launch_bounds__(GS_THREADS)
+gather_rows_smem_kernel(int c, int n, int64_t L, int cb, int64_t chunk, const float *__restrict__ points,
+                        const int *__restrict__ idx, float *__restrict__ out) {
+    extern __shared__ float rows[];            // [cb][n]
+    const int b = blockIdx.z;
+    const int cblk = blockIdx.y * cb;
+    const int nc = min(c, cblk + cb) - cblk;
+    const float *src = points + ((size_t)b * c + cblk) * n;
+    const int64_t tot = (int64_t)nc * n;
+    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (tot % 4 == 0)) {
+        for (int64_t i = threadIdx.x; i < tot / 4; i += GS_THREADS)
+            reinterpret_cast<float4 *>(rows)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+    } else {
+        for (int64_t i = threadIdx.x; i < tot; i += GS_THREADS) rows[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int *ix = idx + (size_t)b * L;
+    float *dst = out + ((size_t)b * c + cblk) * L;
+    const int64_t j0 = (int64_t)blockIdx.x * chunk, j1 = min(L, j0 + chunk);
+    if (VEC4) {
+        for (int64_t j4 = j0 + (int64_t)threadIdx.x * 4; j4 < j1; j4 += GS_THREADS * 4) {
+            const int4 id = __ldg(reinterpret_cast<const int4 *>(ix + j4));
+#pragma unroll 4
+            for (int ci = 0; ci < nc; ++ci) {
+                const float *r = rows + (size_t)ci * n;
+                st_stream4(reinterpret_cast<float4 *>(dst + (size_t)ci * L + j4), make_float4(r[id.x], r[id.y], r[id.z], r[id.w]));
+            }
+        }
+    } else {
+        for (int64_t j = j0 + threadIdx.x; j < j1; j += GS_THREADS) {
+            const int id = __ldg(ix + j);
+            for (int ci = 0; ci < nc; ++ci) st_stream(dst + (size_t)ci * L + j, rows[(size_t)ci * n + id]);
+        }
+    }
+}
+
 // grad_points[b,c,idx[b,j]] += grad_out[b,c,j]
 __global__ void __launch_bounds__(GG_THREADS)
 scatter_add_rows_kernel(int c, int n, int64_t L, const float *__restrict__ grad_out,
@@ -65,6 +112,34 @@ static int launch_gather(const char *name, int b, int c, int n, int64_t L, const
     CAPTRA_REQUIRE(b <= 65535 && ceil_div(c, GG_CH_BLOCK) <= 65535, "%s: grid limit", name);
     const bool vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    // big calls: rows staged in shared memory (about 96 KB per CTA, two CTAs per SM)
+    constexpr size_t kSmemBudget = 96u << 10, kSmemMax = 200u << 10;
+    const int64_t work = (int64_t)b * c * L;
+    if (work >= (int64_t)1 << 22 && L >= 8 * (int64_t)n && (size_t)n * 4 <= kSmemMax) {
+        int cb = (int)std::max<size_t>(1, kSmemBudget / ((size_t)n * 4));
+        cb = std::min(std::min(cb, 32), c);
+        if (c <= 4 && (size_t)c * n * 4 <= kSmemMax) cb = c;   // xyz-like inputs: idx read once for all channels
+        const int nblk = ceil_div(c, cb);
+        cb = ceil_div(c, nblk);                // even out the channel blocks
+        const size_t smem = (size_t)cb * n * 4;
+        // split L only while there are fewer CTAs than two per SM, keeping chunks >= 2 rows' worth of slots
+        int splits = 1;
+        const int64_t ctas = (int64_t)b * nblk;
+        if (ctas < 2 * 148) splits = (int)std::min<int64_t>(ceil_div<int64_t>(2 * 148, ctas), std::max<int64_t>(1, L / (2 * (int64_t)n)));
+        int64_t chunk = ceil_div<int64_t>(ceil_div<int64_t>(L, splits), 4) * 4;
+        splits = (int)ceil_div<int64_t>(L, chunk);
+        if (nblk <= 65535) {
+            auto kern = vec ? gather_rows_smem_kernel<true> : gather_rows_smem_kernel<false>;
+            static size_t attr_smem[2] = {0, 0};
+            if (smem > attr_smem[vec]) {
+                CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+                attr_smem[vec] = kSmemMax;
+            }
+            kern<<<dim3(splits, nblk, b), GS_THREADS, smem, stream>>>(c, n, L, cb, chunk, points, idx, out);
+            CAPTRA_CHECK_LAUNCH(name);
+            return CAPTRA_OK;
+        }
+    }
     if (vec) {
         dim3 grid((unsigned)ceil_div<int64_t>(L / 4, GG_THREADS), ceil_div(c, GG_CH_BLOCK), b);
         gather_rows_kernel<true><<<grid, GG_THREADS, 0, stream>>>(c, n, L, points, idx, out);

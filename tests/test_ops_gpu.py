@@ -195,12 +195,36 @@ def test_empty_batch_and_zero_sizes(futils, cuda):
     assert out.shape == (2, 0, 3, 4)
 
 
+@pytest.mark.parametrize("b,c,n,m,k", [
+    (4, 70, 1000, 256, 64),      # rows staged in shared memory, 16-byte stores, ragged last channel block
+    (3, 33, 1001, 250, 63),      # same with L % 4 != 0 and unaligned rows: scalar variant
+    (1, 3, 16384, 4096, 64),     # BASELINE cfg5 level 1 shape (one cloud): slot range split over CTAs
+    (2, 130, 30000, 2048, 128),  # rows of 120 KB: one channel per CTA
+])
+def test_group_points_large_calls_bit_exact(b, c, n, m, k, futils, oracle, cuda):
+    """Big group_points calls take the shared-memory-staged gather (csrc/group_gather.cu)."""
+    rng = np.random.default_rng(b * 1000 + c)
+    feats = rng.normal(size=(b, c, n)).astype(np.float32)
+    idx = rng.integers(0, n, size=(b, m, k)).astype(np.int32)
+    idx[0, 0, :4] = [0, n - 1, 0, n - 1]
+    want = oracle.grouping_operation(feats, idx)
+    got = futils.grouping_operation(dev(feats, cuda), dev(idx, cuda))
+    assert np.array_equal(got.cpu().numpy(), want)
+    idx1 = np.ascontiguousarray(idx.reshape(b, m * k))
+    got1 = futils.gather_operation(dev(feats, cuda), dev(idx1, cuda))
+    assert np.array_equal(got1.cpu().numpy(), want.reshape(b, c, m * k))
+
+
 @pytest.mark.parametrize("kind,n,m,radius,k", [
-    ("surface", 16384, 512, 0.05, 64),      # BASELINE cfg5 level 1: sparse balls, sorted-candidate path
+    ("surface", 16384, 512, 0.05, 64),      # BASELINE cfg5 level 1: sparse balls, bitmap path
     ("uniform", 12000, 300, 0.08, 32),
     ("surface", 16384, 256, 0.3, 64),       # dense balls: > 512 candidates -> early-exit scan fallback
     ("tiled", 10000, 200, 0.06, 48),        # exact duplicates
     ("surface", 20480, 128, 0.02, 16),      # many empty balls
+    ("surface", 2048, 300, 0.1, 64),        # smallest cloud on the grid path (2 bitmap words per lane)
+    ("uniform", 4096, 1024, 0.1, 64),       # BASELINE cfg5 level 2
+    ("uniform", 70001, 97, 0.03, 40),       # bitmap too big for four warps per CTA: one-warp variant
+    ("surface", 5000, 77, 0.12, 200),       # nsample > hits for most balls, odd sizes
 ])
 def test_ball_query_grid_path_bit_exact(kind, n, m, radius, k, futils, oracle, refcu, cuda):
     """Large clouds take the binned search (csrc/ball_query.cu); same hits, same order as the scan."""
