@@ -28,6 +28,9 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# stdout carries exactly one JSON line: keep NCCL's version/info banner off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
@@ -197,6 +200,18 @@ def cpu_reference_arm(workload, steps, warmup, sample_clouds):
             "sample": "%d of %d clouds per step x %d steps (%d warm-up), oracle/frame_ref.track_step, torch %d threads + OpenMP %d" % (
                 sample_clouds, w["batch"], len(times), warmup, cores, cpu_ref.num_threads()),
             "ms_per_step": 1e3 * total / len(times), "median_ms": 1e3 * float(np.median(times)), "best_ms": 1e3 * float(np.min(times))}
+
+
+def ncu_traffic(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `tag`, from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json); None if that kernel was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            table = json.load(f)
+    except (OSError, ValueError):
+        return None
+    ent = table.get(tag)
+    return None if ent is None else ent["dram_bytes_per_launch"]
 
 
 def main():
@@ -370,12 +385,14 @@ def main():
         tname = _parse(top["tag"])[0]
         if tname in ("sa_mlp_max", "point_mlp"):
             roofline = {"kernel": top["tag"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tf_sus"], "unit": "TFLOP/s",
-                        "frac": top["tflops"] / pk["tf_sus"], "traffic": None,
+                        "frac": top["tflops"] / pk["tf_sus"], "traffic": ncu_traffic(top["tag"]),
+                        "frac_of_split_ceiling": 3.0 * top["tflops"] / pk["tf_sus"] if mlp.DEFAULT_IMPL else None,
+                        "split_note": "impl 1/2 issue three tensor-core products per fp32-accurate MAC, so the reachable ceiling is peak/3",
                         "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step); algorithmic flops = 2*rows*sum(Cin*Cout), each MAC counted once" % pk["src"],
                         "avg_us": top["avg_us"], "share_of_step": top["share_of_step"]}
         else:
             roofline = {"kernel": top["tag"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": top["hbm_frac"], "traffic": None, "peak_source": pk["src"] + " hbm_gbs",
+                        "frac": top["hbm_frac"], "traffic": ncu_traffic(top["tag"]), "peak_source": pk["src"] + " hbm_gbs",
                         "avg_us": top["avg_us"], "share_of_step": top["share_of_step"]}
         bq = [k for k in kernels if _parse(k["tag"])[0] in ("ball_query_multi", "sa_mlp_max")]
         qg_bytes = sum(k["alg_bytes"] * k["launches_per_step"] for k in bq)
