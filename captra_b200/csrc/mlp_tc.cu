@@ -7,6 +7,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace captra {
 using namespace tc;
@@ -93,61 +94,68 @@ __global__ void __launch_bounds__(128) umma_debug_gemm_kernel(int K, int N, cons
 
 
 // ------------------------------------------------------------------------------------------------
-// The fused kernel.
+// The fused kernel (v6: piece-parallel producers).
 //
-// Persistent CTAs walk 128-row tiles.  Warps 0-3 ("row threads", thread r <-> tile row r <-> TMEM
-// lane r) produce the A operand and run the epilogues; warp 4 (one elected thread) issues
-// tcgen05.mma; warp 5 (one elected thread) streams the pre-split weights with bulk-copy TMA.
+// Persistent CTAs walk 128-row tiles.  A K slab is KC = 16*G input channels; producer group g
+// (128 threads: thread r <-> tile row r <-> TMEM lane r) owns the 16-channel PIECE g of EVERY slab, so
+// all 4G producer warps work on the same slab at once: the per-slab latency is one piece, the
+// pipeline restarts quickly at a layer boundary, and 16 (LARGE) / 2x8 (SMALL, two CTAs per SM) warps
+// give the SM enough independent instruction streams to hide the TMEM / L2 / conversion latencies
+// (v5 had 8 warps alternating whole slabs and ran at 0.16 IPC per scheduler, profiles/r01_*).
 //
-//   layer l, K slab s (16 input channels), stage st = slab counter mod NST:
-//     row threads : A slab -> (hi, lo) planes of a_stage[st]
+//   layer l, K slab s, stage st = slab counter mod NST:
+//     producers   : piece g of the A slab -> (hi, lo) planes of a_stage[st]
 //         layer 0 : gathered from global through the index list (SA) or row pointers (dense), with a
-//                   3-slab register prefetch so the L2 gather latency hides behind the MMAs
-//         layer>0 : read straight out of TMEM -- 16 accumulator columns of layer l-1 ARE slab s of
-//                   layer l -- + bias, ReLU, 3xTF32 split.  The epilogue of layer l-1 and the MMAs
-//                   of layer l therefore overlap slab by slab; accumulators ping-pong between two
-//                   TMEM regions and no activation ever touches shared memory in fp32.
+//                   two-slab register prefetch so the L2 gather latency hides behind the MMAs
+//         layer>0 : read straight out of TMEM -- 16 accumulator columns of layer l-1 ARE piece g of
+//                   slab s of layer l -- + bias, ReLU, split.  The epilogue of layer l-1 and the MMAs
+//                   of layer l overlap slab by slab; accumulators ping-pong between two TMEM regions
+//                   and no activation ever touches shared memory in fp32.
 //     TMA thread  : W slab (hi plane | lo plane, pre-split, chunk-major in global) -> w_stage[st]
-//     MMA thread  : 2 k-steps x 3 terms (lo*hi, hi*lo, hi*hi) of tcgen05.mma kind::tf32,
-//                   tcgen05.commit -> empty[st]; after a layer's last slab also -> d_ready
-//   last epilogue : group > 0 -> max over the rows of each group by redux.sync on the (non-negative)
-//                                float bit patterns, one coalesced row write per group
+//     MMA thread  : k-steps x 3 terms (lo*hi, hi*lo, hi*hi) of tcgen05.mma, tcgen05.commit ->
+//                   empty[st]; after a layer's last slab also -> d_ready.  K-steps (and pieces) that
+//                   only carry zero padding are skipped in every layer.
+//   last epilogue : group > 0 -> max over the rows of each group on the RAW accumulators (bias and
+//                                ReLU commute with the max: one fma + max per column instead of per
+//                                element), one coalesced row write per group
 //                   group = 0 -> the thread's row straight to global (point-major)
 //
-// Shared-memory operand layout (K-major, no swizzle): element (row, k) of a 16-channel slab lives at
-//   plane + (k/4) * ROWS*16 + row*16 + (k%4)*4      -> LBO = ROWS*16, SBO = 128 in the descriptors,
-// so thread r writes 16-byte pieces at r*16 (conflict-free) and never touches another row.
+// Shared-memory operand layout (K-major, no swizzle): element (row, k) of a slab lives at
+//   plane + (k / EPC) * ROWS*16 + row*16 + (k % EPC) * sizeof  (EPC = 8 halfs or 4 tf32 per 16-byte
+//   chunk)  -> LBO = ROWS*16, SBO = 128 in the descriptors, so thread r writes 16-byte pieces at
+//   r*16 (conflict-free) and never touches another row.
+//
+// fp16x3 conversion cost matters (it is the producers' inner loop): two elements per F2FP via
+// cvt.*.f16x2.f32.  For layers > 0 the ReLU is folded into the conversion: hi = cvt.rz.relu (round
+// toward zero, so the remainder x - hi is >= 0 for x >= 0 and the .relu on lo = cvt.rn.relu(x - hi)
+// both keeps it and zeroes the x < 0 case, where hi = 0 and x - hi = x < 0).
 // ------------------------------------------------------------------------------------------------
-constexpr int TC_GROUPS = 2;                      // producer groups; group g owns every 2nd slab
-constexpr int TC_PROD = 128 * TC_GROUPS;          // producer / epilogue threads (warps 0-7)
-constexpr int TC_THREADS = TC_PROD + 64;          // + MMA warp (8) + TMA warp (9)
-// A slab is always 8 chunks of 16 bytes per row = 4 k-steps; it spans 32 channels as TF32 (impl 1,
-// 3xTF32) or 64 channels as fp16 (impl 2, "fp16x3": the same hi/lo split with 11-bit mantissas, half
-// the operand bytes and K=16 per MMA; weights are pre-scaled by a power of two per layer so their lo
-// parts stay normal, activations saturate at +-65504).
-constexpr int TC_NCHUNK = 8;
 constexpr int TC_BIAS_PAD = 16;                   // bias region = npad + 16 floats; [npad] = 1 / weight scale
-__host__ __device__ constexpr int tc_kc(bool f16, bool small) { return (f16 ? 64 : 32) / (small ? 2 : 1); }
-constexpr int TC_A_PLANE = TC_NCHUNK * TC_CHUNK_BYTES;   // bytes of one (hi or lo) A slab plane: 16 KB
-constexpr int TC_A_STAGE = 2 * TC_A_PLANE;        // hi + lo
 constexpr int TC_MAX_STAGES = 4;
+// channels per K slab: 8 chunks of 16 bytes per row (LARGE) or 4 (SMALL); a chunk is 8 halfs / 4 tf32
+__host__ __device__ constexpr int tc_kc(bool f16, bool small) { return (f16 ? 64 : 32) / (small ? 2 : 1); }
+__host__ __device__ constexpr int tc_groups(bool f16, bool small) { return tc_kc(f16, small) / 16; }
+__host__ __device__ constexpr int tc_threads(bool f16, bool small) { return 128 * tc_groups(f16, small) + 64; }
 
 struct TcArgs {
     int nlayers, relu_last, cout_last;
     int kpad[CAPTRA_MAX_MLP_LAYERS], npad[CAPTRA_MAX_MLP_LAYERS];
-    const float *wpk[CAPTRA_MAX_MLP_LAYERS];   // [nslab][2 planes][8 chunks][npad][4]
-    const float *bias[CAPTRA_MAX_MLP_LAYERS];  // [npad]
+    int kreal[CAPTRA_MAX_MLP_LAYERS];           // input channels that carry data (cin, then npad[l-1]); the rest of kpad is skipped
+    const float *wpk[CAPTRA_MAX_MLP_LAYERS];   // [nslab][2 planes][NCHUNK][npad][16 bytes]
+    const float *bias[CAPTRA_MAX_MLP_LAYERS];  // [npad + 16]
     int64_t rows, ntiles;
     int group;                                  // max over each `group` rows (32|64|128) or 0
     float *out; int64_t ldo; int col_off;
     int n, s, cfeat; const float *xyz, *new_xyz, *feats; const int *idx;
     const float *segA; int64_t ldA; int ca; const float *segB; int64_t ldB; int cb; int bcast;
     const float *in_scale, *in_shift; int rows_per_cloud;   // dense: x <- relu(x * scale[cloud] + shift[cloud]) on load (GroupNorm + ReLU of the producer layer)
+    int aff_pad;                                // > 0: the tile's scale/shift rows are staged in shared memory (2 * aff_pad floats)
     int wstage_bytes, bias_floats, region_cols, tmem_cols, nst_log2;
     int nsplit, last_npad, cout_total;          // single wide layer split into 256-column chunks over grid.y
     int f16, small;
-    int cin0, klast0;                           // true layer-0 width; k-steps that carry data in layer 0's last slab
-    int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A stores, 2 no W copies, 4 no MMAs, 8 no last epilogue, 32/128 stamps, 64 no gather
+    int cin0;                                   // true layer-0 width
+    int tpose;                                  // grouped max: the last layer is computed transposed (channels in TMEM lanes)
+    int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A production, 2 no W copies, 4 no MMAs, 64 no layer-0 gather, 32 phase stamps
 };
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t *smem_result, uint32_t ncols) {
@@ -168,7 +176,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // fp16 operands saturate at +-65504.  A value that large is recorded in g_f16_overflow so the host can
 // detect the (never observed) case and re-run on the 3xTF32 path (captra_f16_overflow_flag).
 __device__ int g_f16_overflow;
-// x -> (hi, lo) as two fp16 numbers (hi = rn(x), lo = rn(x - hi)): 22 mantissa bits together
+// x -> (hi, lo) as two fp16 numbers (hi = rn(x), lo = rn(x - hi)): 22 mantissa bits together (weights)
 __device__ __forceinline__ void split_f16(float x, unsigned short &hi, unsigned short &lo) {
     unsigned short h, l;
     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
@@ -176,6 +184,19 @@ __device__ __forceinline__ void split_f16(float x, unsigned short &hi, unsigned 
     asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
     asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(x - hf));
     hi = h; lo = l;
+}
+// Two activations -> packed (hi, lo) f16x2 words (element 0 in the low half).  RELU = false: hi = rn(x),
+// lo = rn(x - hi) (signed inputs of layer 0).  RELU = true: the split of max(x, 0) with the ReLU folded
+// into the conversions (see the header comment).  x - hi is exact in fp32 either way.
+template <bool RELU>
+__device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t &hi2, uint32_t &lo2) {
+    if (RELU) asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(x1), "f"(x0));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(x1), "f"(x0));
+    float h0, h1;
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi2));
+    const float d0 = __fsub_rn(x0, h0), d1 = __fsub_rn(x1, h1);
+    if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(d1), "f"(d0));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(d1), "f"(d0));
 }
 // Max over the 32 lanes of a warp for 16 values per lane in 16 shuffles (recursive halving): after
 // the four halving rounds lane l holds column ((l&1)<<3 | (l&2)<<1 | (l&4)>>1 | (l&8)>>3); a final
@@ -205,18 +226,11 @@ __device__ __forceinline__ float warp_colmax16(const float (&x)[16], int lane, i
     col = (b0 ? 8 : 0) | (b1 ? 4 : 0) | (b2 ? 2 : 0) | (b3 ? 1 : 0);
     return v;
 }
-__device__ __forceinline__ uint32_t pack2(unsigned short a, unsigned short b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
-// timing probe: producer thread 0 of CTA 0 stamps clock64() at phase boundaries of its first tiles
+// timing probe (CAPTRA_TC_DBG bit 32): producer thread 0 of CTA 0 stamps clock64() at phase
+// boundaries of its first tiles; read back with captra_debug_tc_timestamps
 __device__ long long g_tc_ts[512];
 __device__ int g_tc_ts_n;
-#define TC_STAMP_T(code, T)                                                         \
-    do {                                                                            \
-        if ((a.dbg & (T)) && blockIdx.x == 0 && blockIdx.y == 0) {                  \
-            const int i__ = g_tc_ts_n;                                              \
-            if (i__ < 255) { g_tc_ts[2 * i__] = clock64(); g_tc_ts[2 * i__ + 1] = (code); g_tc_ts_n = i__ + 1; } \
-        }                                                                           \
-    } while (0)
 #define TC_STAMP(code)                                                              \
     do {                                                                            \
         if ((a.dbg & 32) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {       \
@@ -225,37 +239,39 @@ __device__ int g_tc_ts_n;
         }                                                                           \
     } while (0)
 
-// What bounds this kernel (clock64 probes, profiles/r01_tc_probe.txt): the single MMA-issuing thread.
-// One tcgen05.mma costs it ~80 cycles to issue and one barrier round (two try_waits + commit) ~450,
-// while a kind::tf32 MMA of N=128 is only 64 tensor-pipe cycles.  Hence: 32-channel slabs (12 MMAs
-// per barrier round), ONE `full` barrier per stage shared by the A producers and the weight TMA
-// (4 warp arrivals + 1 arrive.expect_tx), descriptors advanced by adding to their low word, and
-// two producer groups that alternate slabs so their per-slab latency chains overlap.
-//
-// Two shapes of the same kernel.  LARGE (wide layers): 320 threads, two producer groups alternating
-// 8-chunk slabs, one CTA per SM.  SMALL (every layer <= 128 columns: the sa1 scales, fp1): the tile
-// time is a chain of latencies (gather, MMA drain, TMEM read, epilogue), not throughput, so the CTA
-// shrinks to one producer group and 4-chunk slabs (192 threads, 64 KB, 256 TMEM columns) and TWO CTAs
-// share an SM, each on its own tile.
+// one 16-channel piece of one row, split into the two operand planes
+template <bool F16>
+struct TcPiece {
+    uint32_t hi[F16 ? 8 : 16], lo[F16 ? 8 : 16];
+};
+
+// Two shapes of the same kernel.  LARGE (a layer wider than 128 columns): 8-chunk slabs, G = 4 (fp16x3)
+// or 2 (3xTF32) producer groups, one CTA per SM.  SMALL (every layer <= 128 columns: the sa1 scales,
+// fp1): 4-chunk slabs, G = 2 / 1, 64 KB and 256 TMEM columns per CTA so TWO CTAs share an SM and one
+// tile's epilogue overlaps the other's MMAs.
 template <int MODE, bool F16, bool SMALL>  // MODE 0: SA gather loader, 1: dense-row loader; the last epilogue is chosen by a.group
-__global__ void __launch_bounds__(SMALL ? 192 : 320, SMALL ? 2 : 1) mlp_tc_kernel(const TcArgs a) {
-    constexpr int TC_GROUPS = SMALL ? 1 : 2;
-    constexpr int TC_PROD = 128 * TC_GROUPS;
-    constexpr int TC_THREADS = TC_PROD + 64;
-    constexpr int TC_NCHUNK = SMALL ? 4 : 8;
-    constexpr int TC_A_PLANE = TC_NCHUNK * TC_CHUNK_BYTES;
-    constexpr int TC_A_STAGE = 2 * TC_A_PLANE;
-    constexpr int TC_KC = tc_kc(F16, SMALL);
-    constexpr int PIECES = TC_KC / 16;             // 16-channel pieces per slab
+__global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_kernel(const TcArgs a) {
+    constexpr int G = tc_groups(F16, SMALL);
+    constexpr int PROD = 128 * G;                  // producer / epilogue threads (warps 0 .. 4G-1)
+    constexpr int NTHREADS = PROD + 64;            // + MMA warp (4G) + TMA warp (4G+1)
+    constexpr int NCHUNK = SMALL ? 4 : 8;
+    constexpr int A_PLANE = NCHUNK * TC_CHUNK_BYTES;   // bytes of one (hi or lo) A slab plane
+    constexpr int A_STAGE = 2 * A_PLANE;
+    constexpr int KC = tc_kc(F16, SMALL);
+    constexpr int KMMA = F16 ? 16 : 8;             // K of one tcgen05.mma (32 bytes per row)
+    constexpr int KSTEPS = KC / KMMA;              // == NCHUNK / 2
+    static_assert(KC == 16 * G && KSTEPS == NCHUNK / 2, "one 16-channel piece per producer group");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], d_ready;
     __shared__ uint32_t tmem_base_s;
 
     const uint32_t nst_log2 = (uint32_t)a.nst_log2, NST = 1u << nst_log2;
-    uint8_t *a_stage = smem_raw;                                          // NST x TC_A_STAGE
-    uint8_t *w_stage = a_stage + (size_t)NST * TC_A_STAGE;                // NST x wstage_bytes
+    uint8_t *a_stage = smem_raw;                                          // NST x A_STAGE
+    uint8_t *w_stage = a_stage + (size_t)NST * A_STAGE;                   // NST x wstage_bytes
     float *bias_s = reinterpret_cast<float *>(w_stage + (size_t)NST * a.wstage_bytes);
-    float *red = reinterpret_cast<float *>(a_stage);                      // [4][256], aliases stage 0 (idle in the last epilogue)
+    float *aff_s = bias_s + a.bias_floats;                                // [2][aff_pad] when a.aff_pad > 0
+    float *red = aff_s + 2 * a.aff_pad;                                   // [4][256] partial maxima of the grouped epilogue (also the slack the
+                                                                          // transposed last layer's 128-row weight reads may run into)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(SMALL ? 192 : 320, SMALL ? 2 : 1) mlp_tc_kerne
     if (a.nsplit > 1) {
         const int y = blockIdx.y;
         npad_y = (y < a.nsplit - 1) ? 256 : a.last_npad;
-        wpk0 += (size_t)y * (a.kpad[0] / TC_KC) * 2 * TC_NCHUNK * 256 * 4;
+        wpk0 += (size_t)y * (a.kpad[0] / KC) * 2 * NCHUNK * 256 * 4;
         bias0 += y * (256 + TC_BIAS_PAD);
         col_off += y * 256;
         cout_last = min(256, a.cout_total - y * 256);
@@ -274,16 +290,16 @@ __global__ void __launch_bounds__(SMALL ? 192 : 320, SMALL ? 2 : 1) mlp_tc_kerne
     auto WPK = [&](int l) { return l == 0 ? wpk0 : a.wpk[l]; };
     auto BIAS = [&](int l) { return l == 0 ? bias0 : a.bias[l]; };
 
-    if (warp == TC_PROD / 32) tmem_alloc_dyn(&tmem_base_s, (uint32_t)a.tmem_cols);
+    if (warp == PROD / 32) tmem_alloc_dyn(&tmem_base_s, (uint32_t)a.tmem_cols);
     if (tid == 0) {
-        for (uint32_t i = 0; i < NST; ++i) { mbar_init(&full[i], 4 + 1); mbar_init(&empty[i], 1); }
+        for (uint32_t i = 0; i < NST; ++i) { mbar_init(&full[i], 4 * G + 1); mbar_init(&empty[i], 1); }
         mbar_init(&d_ready, 1);
         fence_mbar_init();
     }
     {   // biases of all layers -> smem
         int off = 0;
         for (int l = 0; l < a.nlayers; ++l) {
-            for (int i = tid; i < NPAD(l) + TC_BIAS_PAD; i += TC_THREADS) bias_s[off + i] = __ldg(BIAS(l) + i);
+            for (int i = tid; i < NPAD(l) + TC_BIAS_PAD; i += NTHREADS) bias_s[off + i] = __ldg(BIAS(l) + i);
             off += NPAD(l) + TC_BIAS_PAD;
         }
     }
@@ -291,130 +307,166 @@ __global__ void __launch_bounds__(SMALL ? 192 : 320, SMALL ? 2 : 1) mlp_tc_kerne
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    // Role dispatch on a provably warp-uniform warp index: the MMA and TMA warps run their loops
+    // converged and elect one lane only around the issue itself, so descriptors and counters stay in
+    // uniform registers.  (With `if (tid == X)` the compiler wrapped every tcgen05.mma in an
+    // ELECT / 5x R2UR / BRA.U.ANY waterfall: ~80 cycles per MMA against 64 tensor cycles at N = 128.)
+    const int warp_u = __shfl_sync(kFull, warp, 0);
 
-    if (tid == TC_PROD) {
+    if (warp_u == PROD / 32) {
         // ===================== MMA issuer =====================
         uint32_t it = 0;
         const uint64_t a_desc0 = smem_desc_kmajor_noswz(smem_u32(a_stage), TC_CHUNK_BYTES, 128);
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             for (int l = 0; l < a.nlayers; ++l) {
-                const int nslab = a.kpad[l] / TC_KC;
+                const int nslab = a.kpad[l] / KC;
                 const uint32_t npad = (uint32_t)NPAD(l);
                 const uint32_t idesc = make_idesc(F16 ? 0 : 2, TC_ROWS, (int)npad);
+                const uint32_t idesc_t = make_idesc(F16 ? 0 : 2, TC_ROWS, TC_ROWS);
+                const bool tpose_l = a.tpose && l == a.nlayers - 1;
+                const uint32_t nblk = (npad + 127u) / 128u;
                 const uint32_t b_lbo = npad * 16;
                 const uint64_t b_desc0 = smem_desc_kmajor_noswz(smem_u32(w_stage), b_lbo, 128);
-                const uint32_t b_lo_off = (TC_NCHUNK * b_lbo) >> 4, b_step = (2 * b_lbo) >> 4;   // in 16-byte units
+                const uint32_t b_lo_off = (NCHUNK * b_lbo) >> 4, b_step = (2 * b_lbo) >> 4;   // in 16-byte units
                 const uint32_t tmem_d = tmem_base + (uint32_t)((l & 1) * a.region_cols);
-                for (int s = 0; s < nslab; ++s, ++it) {
+                int krem = a.kreal[l];                                  // channels with data left in this layer
+                for (int s = 0; s < nslab; ++s, ++it, krem -= KC) {
                     const uint32_t st = it & (NST - 1), ph = (it >> nst_log2) & 1;
-                    TC_STAMP_T(40, 128);
-                    mbar_wait(&full[st], ph);
+                    mbar_wait_warp(&full[st], ph);
                     tcgen05_fence_after();
-                    TC_STAMP_T(42, 128);
                     // descriptors of this stage: only the 14-bit start-address field (16-byte units) moves
-                    uint64_t ah = a_desc0 + (uint64_t)((st * TC_A_STAGE) >> 4);
-                    uint64_t al = ah + (TC_A_PLANE >> 4);
+                    uint64_t ah = a_desc0 + (uint64_t)((st * A_STAGE) >> 4);
+                    uint64_t al = ah + (A_PLANE >> 4);
                     uint64_t bh = b_desc0 + (uint64_t)((st * (uint32_t)a.wstage_bytes) >> 4);
                     uint64_t bl = bh + b_lo_off;
-                    const int nks = (l == 0 && s == nslab - 1) ? a.klast0 : TC_NCHUNK / 2;   // zero padding needs no MMAs
-#pragma unroll
-                    for (int j = 0; j < TC_NCHUNK / 2; ++j) {
-                        if ((a.dbg & 4) || j >= nks) break;
-                        if (F16) {
-                            umma_f16(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
-                            umma_f16(tmem_d, ah, bl, idesc, 1u);
-                            umma_f16(tmem_d, ah, bh, idesc, 1u);
+                    const int nks = min(KSTEPS, (krem + KMMA - 1) / KMMA);   // zero padding needs no MMAs
+                    if (elect_one()) {
+                        if (tpose_l) {
+                            // D^T[channel, point] += W_blk[128 x K] * A[128 points x K]^T: the weights take the A
+                            // role (one 128-row block of output channels per MMA, 2048 bytes apart inside a
+                            // chunk), the activation slab the B role (N = 128 points).  Lanes = channels, so
+                            // the max over a centroid's points is a per-thread reduction in the epilogue.
+    #pragma unroll
+                            for (int j = 0; j < KSTEPS; ++j) {
+                                if (j >= nks || (a.dbg & 4)) break;
+                                for (uint32_t cb = 0; cb < nblk; ++cb) {
+                                    const uint32_t dT = tmem_d + cb * 128u;
+                                    const uint64_t wo = (uint64_t)(cb * 128u);        // 128 rows * 16 bytes, in 16-byte units
+                                    if (F16) {
+                                        umma_f16(dT, bh + wo, al, idesc_t, (s | j) ? 1u : 0u);
+                                        umma_f16(dT, bl + wo, ah, idesc_t, 1u);
+                                        umma_f16(dT, bh + wo, ah, idesc_t, 1u);
+                                    } else {
+                                        umma_tf32(dT, bh + wo, al, idesc_t, (s | j) ? 1u : 0u);
+                                        umma_tf32(dT, bl + wo, ah, idesc_t, 1u);
+                                        umma_tf32(dT, bh + wo, ah, idesc_t, 1u);
+                                    }
+                                }
+                                ah += (2 * TC_CHUNK_BYTES) >> 4; al += (2 * TC_CHUNK_BYTES) >> 4;
+                                bh += b_step; bl += b_step;
+                            }
                         } else {
-                            umma_tf32(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
-                            umma_tf32(tmem_d, ah, bl, idesc, 1u);
-                            umma_tf32(tmem_d, ah, bh, idesc, 1u);
+    #pragma unroll
+                            for (int j = 0; j < KSTEPS; ++j) {
+                                if (j >= nks || (a.dbg & 4)) break;
+                                if (F16) {
+                                    umma_f16(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
+                                    umma_f16(tmem_d, ah, bl, idesc, 1u);
+                                    umma_f16(tmem_d, ah, bh, idesc, 1u);
+                                } else {
+                                    umma_tf32(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
+                                    umma_tf32(tmem_d, ah, bl, idesc, 1u);
+                                    umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                                }
+                                ah += (2 * TC_CHUNK_BYTES) >> 4; al += (2 * TC_CHUNK_BYTES) >> 4;
+                                bh += b_step; bl += b_step;
+                            }
                         }
-                        ah += (2 * TC_CHUNK_BYTES) >> 4; al += (2 * TC_CHUNK_BYTES) >> 4;
-                        bh += b_step; bl += b_step;
+                        umma_commit(&empty[st]);
+                        if (s == nslab - 1) umma_commit(&d_ready);
                     }
-                    TC_STAMP_T(43, 128);
-                    umma_commit(&empty[st]);
-                    if (s == nslab - 1) umma_commit(&d_ready);
+                    __syncwarp();
                 }
             }
         }
-    } else if (tid == TC_PROD + 32) {
+    } else if (warp_u == PROD / 32 + 1) {
         // ===================== weight producer (bulk-copy TMA) =====================
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             for (int l = 0; l < a.nlayers; ++l) {
-                const int nslab = a.kpad[l] / TC_KC;
-                const uint32_t bytes = 2u * TC_NCHUNK * (uint32_t)NPAD(l) * 16u;
+                const int nslab = a.kpad[l] / KC;
+                const uint32_t bytes = 2u * NCHUNK * (uint32_t)NPAD(l) * 16u;
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(WPK(l));
                 for (int s = 0; s < nslab; ++s, ++it) {
                     const uint32_t st = it & (NST - 1), ph = (it >> nst_log2) & 1;
-                    mbar_wait(&empty[st], ph ^ 1);
-                    if (a.dbg & 2) {
-                        mbar_arrive(&full[st]);
-                    } else {
-                        mbar_arrive_expect_tx(&full[st], bytes);
-                        bulk_g2s(w_stage + (size_t)st * a.wstage_bytes, src + (size_t)s * bytes, bytes, &full[st]);
+                    mbar_wait_warp(&empty[st], ph ^ 1);
+                    if (elect_one()) {
+                        if (a.dbg & 2) {
+                            mbar_arrive(&full[st]);
+                        } else {
+                            mbar_arrive_expect_tx(&full[st], bytes);
+                            bulk_g2s(w_stage + (size_t)st * a.wstage_bytes, src + (size_t)s * bytes, bytes, &full[st]);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
-    } else if (tid < TC_PROD) {
+    } else {
         // ===================== producer / epilogue threads =====================
         const int r = tid & 127;              // tile row == TMEM lane
-        const int g = tid >> 7;               // producer group
+        const int g = tid >> 7;               // producer group == piece of every slab
+        const int cg = 16 * g;                // first channel of this thread's piece within a slab
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        uint32_t base = 0;                    // global index of the current layer's slab 0
+        // this thread's 16 bytes of chunk 0 of its piece in stage 0 (hi plane)
+        uint8_t *const my_a = a_stage + (size_t)(F16 ? 2 * g : 4 * g) * TC_CHUNK_BYTES + r * 16;
+        uint32_t it = 0;                      // global slab counter (the same sequence in every role)
         uint32_t dl = 0;
         float amax = 0.f;                     // largest |operand| this thread converted to fp16
+        int aff_cloud = -1;                   // cloud whose scale/shift rows sit in aff_s
 
         auto warp_wait = [&](uint64_t *bar, uint32_t parity) {   // one lane polls, the warp follows
             if (lane == 0) mbar_wait(bar, parity);
             __syncwarp();
         };
-        // store 16 channels (piece `pc` of the slab) of global slab `it` as hi/lo operand planes
-        auto store16 = [&](uint32_t it, int pc, const float4 (&v)[4]) {
-            if (a.dbg & 1) return;
-            const uint32_t st = it & (NST - 1);
-            float *plane_hi = reinterpret_cast<float *>(a_stage + st * TC_A_STAGE) + r * 4;
-            float *plane_lo = plane_hi + TC_A_PLANE / 4;
-            if (F16) {        // 2 chunks of 8 halfs
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const float e[8] = {v[2 * q].x, v[2 * q].y, v[2 * q].z, v[2 * q].w, v[2 * q + 1].x, v[2 * q + 1].y, v[2 * q + 1].z, v[2 * q + 1].w};
-                    unsigned short hh[8], ll[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        split_f16(e[j], hh[j], ll[j]);
-                        amax = fmaxf(amax, fabsf(e[j]));      // saturation watch, checked once per tile
-                    }
-                    const int chunk = 2 * pc + q;
-                    *reinterpret_cast<uint4 *>(plane_hi + chunk * (TC_ROWS * 4)) =
-                        make_uint4(pack2(hh[0], hh[1]), pack2(hh[2], hh[3]), pack2(hh[4], hh[5]), pack2(hh[6], hh[7]));
-                    *reinterpret_cast<uint4 *>(plane_lo + chunk * (TC_ROWS * 4)) =
-                        make_uint4(pack2(ll[0], ll[1]), pack2(ll[2], ll[3]), pack2(ll[4], ll[5]), pack2(ll[6], ll[7]));
-                }
-            } else {          // 4 chunks of 4 floats
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 hh, ll;
-                    split_tf32(v[q].x, hh.x, ll.x); split_tf32(v[q].y, hh.y, ll.y);
-                    split_tf32(v[q].z, hh.z, ll.z); split_tf32(v[q].w, hh.w, ll.w);
-                    const int chunk = 4 * pc + q;
-                    *reinterpret_cast<float4 *>(plane_hi + chunk * (TC_ROWS * 4)) = hh;
-                    *reinterpret_cast<float4 *>(plane_lo + chunk * (TC_ROWS * 4)) = ll;
-                }
-            }
+        auto acquire = [&](uint32_t i) {      // wait until the MMAs that last read this slab's stage are done
+            warp_wait(&empty[i & (NST - 1)], ((i >> nst_log2) & 1) ^ 1);
         };
-        auto acquire = [&](uint32_t it) {     // wait until the MMAs that last read this slab's stage are done
-            warp_wait(&empty[it & (NST - 1)], ((it >> nst_log2) & 1) ^ 1);
-        };
-        auto release = [&](uint32_t it) {     // hand the filled stage to the MMA thread
+        auto release = [&](uint32_t i) {      // hand the filled stage to the MMA thread
             // every writer fences its own generic-proxy stores towards the async proxy; one elected
             // lane per warp then arrives
             fence_proxy_async_smem();
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[it & (NST - 1)]);
+            if (lane == 0) mbar_arrive(&full[i & (NST - 1)]);
+        };
+        // 16 fp32 values -> operand planes.  RELU: the values are pre-activation (layers > 0).
+        auto convert = [&](const float (&x)[16], auto relu_tag, TcPiece<F16> &p) {
+            constexpr bool RELU = decltype(relu_tag)::value;
+            if (F16) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    split2_f16<RELU>(x[2 * j], x[2 * j + 1], p.hi[j], p.lo[j]);
+                    amax = RELU ? fmaxf(fmaxf(amax, x[2 * j]), x[2 * j + 1])      // saturation watch, checked once per kernel
+                                : fmaxf(fmaxf(amax, fabsf(x[2 * j])), fabsf(x[2 * j + 1]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float hi, lo;
+                    split_tf32(RELU ? fmaxf(x[j], 0.f) : x[j], hi, lo);
+                    p.hi[j] = __float_as_uint(hi); p.lo[j] = __float_as_uint(lo);
+                }
+            }
+        };
+        auto store_piece = [&](uint32_t i, const TcPiece<F16> &p) {
+            uint8_t *hi = my_a + (size_t)(i & (NST - 1)) * A_STAGE, *lo = hi + A_PLANE;
+            constexpr int NQ = F16 ? 2 : 4;   // 16-byte chunks per piece
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                *reinterpret_cast<uint4 *>(hi + q * TC_CHUNK_BYTES) = make_uint4(p.hi[4 * q], p.hi[4 * q + 1], p.hi[4 * q + 2], p.hi[4 * q + 3]);
+                *reinterpret_cast<uint4 *>(lo + q * TC_CHUNK_BYTES) = make_uint4(p.lo[4 * q], p.lo[4 * q + 1], p.lo[4 * q + 2], p.lo[4 * q + 3]);
+            }
         };
 
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -439,154 +491,199 @@ __global__ void __launch_bounds__(SMALL ? 192 : 320, SMALL ? 2 : 1) mlp_tc_kerne
                     brow = a.segB ? a.segB + (a.bcast ? grow / a.bcast : grow) * a.ldB : nullptr;
                 }
             }
-            const float *nsc = nullptr, *nsh = nullptr;   // per-cloud affine of the input (dense mode)
-            if (MODE == 1 && a.in_scale && valid) {
-                const int64_t cloud = grow / a.rows_per_cloud;
-                nsc = a.in_scale + cloud * a.ca;
-                nsh = a.in_shift + cloud * a.ca;
+            if (MODE == 1 && a.in_scale) {
+                // a tile lies inside one cloud (rows_per_cloud % 128 == 0, checked on the host): stage the
+                // cloud's scale/shift rows (GroupNorm + ReLU of the producer layer) in shared memory
+                const int cloud = (int)((tile * TC_ROWS) / a.rows_per_cloud);
+                if (cloud != aff_cloud) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(PROD) : "memory");   // everyone is done with the previous rows
+                    for (int i = tid; i < a.aff_pad; i += PROD) {
+                        aff_s[i] = i < a.ca ? __ldg(a.in_scale + (size_t)cloud * a.ca + i) : 0.f;
+                        aff_s[a.aff_pad + i] = i < a.ca ? __ldg(a.in_shift + (size_t)cloud * a.ca + i) : 0.f;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(PROD) : "memory");
+                    aff_cloud = cloud;
+                }
             }
-            auto in0 = [&](int c) -> float {     // layer-0 input element c of this row
-                if (!valid) return 0.f;
-                if (MODE == 0) {
-                    if (c < a.cfeat) return __ldg(frow + c);
-                    const int e = c - a.cfeat;
-                    return e == 0 ? px : (e == 1 ? py : (e == 2 ? pz : 0.f));
-                } else {
-                    if (c < a.ca) return __ldg(arow + c);
-                    if (c < a.ca + a.cb) return __ldg(brow + (c - a.ca));
-                    return 0.f;
-                }
-            };
-            const int nvec = MODE == 0 ? a.cfeat : a.ca;           // leading segment length
-            const float *vbase = MODE == 0 ? frow : arow;
-            const bool vec_row = valid && vbase && ((reinterpret_cast<uintptr_t>(vbase) & 15) == 0);
-            auto load16 = [&](int c0, float4 (&v)[4]) {             // 16 consecutive layer-0 channels
-                if (c0 >= a.cin0) {   // pure padding
+            auto load_piece = [&](int c0, float (&x)[16]) {            // 16 consecutive layer-0 channels from c0
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    return;
-                }
-                if (a.dbg & 64) {   // probe: no global gather
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = make_float4(px, py, pz, 1.f);
-                    return;
-                }
-                if (vec_row && c0 + 16 <= nvec) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4 *>(vbase + c0) + q);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        v[q] = make_float4(in0(c0 + 4 * q), in0(c0 + 4 * q + 1), in0(c0 + 4 * q + 2), in0(c0 + 4 * q + 3));
-                }
-                if (MODE == 1 && nsc) {
+                for (int j = 0; j < 16; ++j) x[j] = 0.f;
+                if (!valid || c0 >= a.cin0 || (a.dbg & 65)) return;   // padding rows / channels (probes: no gather)
+                // segment base pointers moved to channel c0, so every element is base + constant
+                const float *pa = MODE == 0 ? frow + c0 : arow + c0;
+                const float *pb = MODE == 0 ? nullptr : brow + (c0 - a.ca);
+                const int na = (MODE == 0 ? a.cfeat : a.ca) - c0;     // channels of the leading segment left from c0
+                const int nb = MODE == 0 ? 3 : a.cb;                  // SA: dx, dy, dz follow the features
+                const float *vp = nullptr;                            // 16 contiguous, 16-byte aligned floats?
+                if (na >= 16) vp = pa;
+                else if (MODE == 1 && na <= 0 && na + nb >= 16) vp = pb;
+                if (vp && (reinterpret_cast<uintptr_t>(vp) & 15) == 0) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float *e = reinterpret_cast<float *>(&v[q]);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int c = c0 + 4 * q + j;
-                            e[j] = c < a.ca ? fmaxf(fmaf(e[j], __ldg(nsc + c), __ldg(nsh + c)), 0.f) : 0.f;
-                        }
+                        const float4 t = __ldg(reinterpret_cast<const float4 *>(vp) + q);
+                        x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (j < na) x[j] = __ldg(pa + j);
+                        else if (j < na + nb) x[j] = MODE == 0 ? (j == na ? px : (j == na + 1 ? py : pz)) : __ldg(pb + j);
+                    }
+                }
+            };
+            // GroupNorm + ReLU of the producer layer, applied to a loaded piece (dense mode)
+            auto affine_piece = [&](int c0, float (&x)[16]) {
+                if (MODE != 1 || !a.in_scale || !valid || c0 >= a.cin0) return;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(aff_s + c0 + 4 * q);
+                    const float4 sh = *reinterpret_cast<const float4 *>(aff_s + a.aff_pad + c0 + 4 * q);
+                    x[4 * q] = fmaxf(fmaf(x[4 * q], sc.x, sh.x), 0.f);
+                    x[4 * q + 1] = fmaxf(fmaf(x[4 * q + 1], sc.y, sh.y), 0.f);
+                    x[4 * q + 2] = fmaxf(fmaf(x[4 * q + 2], sc.z, sh.z), 0.f);
+                    x[4 * q + 3] = fmaxf(fmaf(x[4 * q + 3], sc.w, sh.w), 0.f);
                 }
             };
             TC_STAMP(1);
-            // ---------------- layer 0: this group's slabs; each piece's registers are refilled with the
-            // same piece of the group's NEXT slab right after it is stored (one-slab-ahead prefetch) ----
+            // ---------------- layer 0: piece g of every slab, gathered two slabs ahead ----------------
             {
-                const int nslab = a.kpad[0] / TC_KC;
-                int s = (int)((g - base) & (TC_GROUPS - 1));      // first slab of this layer owned by group g
-                float4 cur[PIECES][4];
-                if (s < nslab) {
-#pragma unroll
-                    for (int pc = 0; pc < PIECES; ++pc) load16(s * TC_KC + 16 * pc, cur[pc]);
-                }
-                for (; s < nslab; s += TC_GROUPS) {
-                    const bool more = s + TC_GROUPS < nslab;
-                    acquire(base + s);
-#pragma unroll
-                    for (int pc = 0; pc < PIECES; ++pc) {
-                        store16(base + s, pc, cur[pc]);
-                        if (more) load16((s + TC_GROUPS) * TC_KC + 16 * pc, cur[pc]);
+                const int nslab = a.kpad[0] / KC, kreal = a.kreal[0];
+                float b0[16], b1[16];
+                load_piece(cg, b0);
+                if (nslab > 1) load_piece(KC + cg, b1);
+                auto step = [&](int s, float (&buf)[16]) {   // buf holds slab s and is refilled with slab s + 2
+                    const int c0 = s * KC + cg;
+                    const bool active = c0 < kreal && !(a.dbg & 1);   // else: pure padding, the MMA thread skips these k-steps
+                    acquire(it);
+                    if (active) {
+                        TcPiece<F16> p;
+                        affine_piece(c0, buf);
+                        convert(buf, std::false_type{}, p);
+                        store_piece(it, p);
                     }
-                    release(base + s);
+                    release(it);
+                    // refill only now: the proxy fence in release() waits for the thread's outstanding
+                    // loads, which would put the L2 latency of the prefetch on every slab's critical path
+                    if (s + 2 < nslab) load_piece(c0 + 2 * KC, buf);
+                    ++it;
+                };
+                for (int s = 0; s < nslab; s += 2) {
+                    step(s, b0);
+                    if (s + 1 < nslab) step(s + 1, b1);
                 }
-                base += nslab;
             }
             TC_STAMP(2);
             // ---------------- layers 1..L-1: previous accumulator -> next operand ----------------
             int bias_off = 0;
             for (int l = 1; l < a.nlayers; ++l) {
-                const int nslab = a.kpad[l] / TC_KC;          // == NPAD(l-1) / TC_KC
-                const uint32_t tsrc = tmem_base + (uint32_t)(((l - 1) & 1) * a.region_cols) + lane_addr;
-                const float *bz = bias_s + bias_off;
-                const float inv = bz[NPAD(l - 1)];            // 1 / weight scale of layer l-1
-                int s = (int)((g - base) & (TC_GROUPS - 1));
+                const int nslab = a.kpad[l] / KC, kreal = a.kreal[l];     // kreal == NPAD(l-1)
+                const uint32_t tsrc = tmem_base + (uint32_t)(((l - 1) & 1) * a.region_cols) + lane_addr + (uint32_t)cg;
+                const float *bz = bias_s + bias_off + cg;
+                const float inv = bias_s[bias_off + NPAD(l - 1)];         // 1 / weight scale of layer l-1
                 warp_wait(&d_ready, dl & 1);
                 ++dl;
                 tcgen05_fence_after();
                 TC_STAMP(10 + l);
                 uint32_t v[16];
-                if (s < nslab) tmem_ld_32x16(tsrc + (uint32_t)(TC_KC * s), v);
-                for (; s < nslab; s += TC_GROUPS) {
-                    acquire(base + s);
-#pragma unroll
-                    for (int pc = 0; pc < PIECES; ++pc) {
+                if (cg < kreal && !(a.dbg & 1)) tmem_ld_32x16(tsrc, v);
+                for (int s = 0; s < nslab; ++s, ++it) {
+                    const int c0 = s * KC + cg;
+                    const bool active = c0 < kreal && !(a.dbg & 1);
+                    TcPiece<F16> p;
+                    if (active) {
                         tmem_ld_wait();
-                        float4 x[4];
+                        float x[16];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 b4 = *reinterpret_cast<const float4 *>(bz + s * TC_KC + 16 * pc + 4 * q);
-                            x[q].x = fmaxf(fmaf(__uint_as_float(v[4 * q + 0]), inv, b4.x), 0.f);
-                            x[q].y = fmaxf(fmaf(__uint_as_float(v[4 * q + 1]), inv, b4.y), 0.f);
-                            x[q].z = fmaxf(fmaf(__uint_as_float(v[4 * q + 2]), inv, b4.z), 0.f);
-                            x[q].w = fmaxf(fmaf(__uint_as_float(v[4 * q + 3]), inv, b4.w), 0.f);
+                            const float4 b4 = *reinterpret_cast<const float4 *>(bz + s * KC + 4 * q);
+                            x[4 * q + 0] = fmaf(__uint_as_float(v[4 * q + 0]), inv, b4.x);
+                            x[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), inv, b4.y);
+                            x[4 * q + 2] = fmaf(__uint_as_float(v[4 * q + 2]), inv, b4.z);
+                            x[4 * q + 3] = fmaf(__uint_as_float(v[4 * q + 3]), inv, b4.w);
                         }
-                        // overlap the next TMEM read: next piece of this slab, else the group's next slab
-                        if (pc + 1 < PIECES) tmem_ld_32x16(tsrc + (uint32_t)(TC_KC * s + 16 * (pc + 1)), v);
-                        else if (s + TC_GROUPS < nslab) tmem_ld_32x16(tsrc + (uint32_t)(TC_KC * (s + TC_GROUPS)), v);
-                        store16(base + s, pc, x);
+                        // overlap the next TMEM read with the conversion (the empty asm pins the fmas
+                        // before it, so the compiler does not copy v to keep the old values alive)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) asm volatile("" : "+f"(x[j]));
+                        if (s + 1 < nslab && c0 + KC < kreal) tmem_ld_32x16(tsrc + (uint32_t)((s + 1) * KC), v);
+                        convert(x, std::true_type{}, p);
                     }
-                    release(base + s);
+                    acquire(it);
+                    if (active) store_piece(it, p);
+                    release(it);
                 }
-                base += nslab;
                 bias_off += NPAD(l - 1) + TC_BIAS_PAD;
                 TC_STAMP(20 + l);
             }
-            // ---------------- last epilogue: the groups alternate 16-column chunks ----------------
+            // ---------------- last epilogue ----------------
             {
                 const int l = a.nlayers - 1;
                 const int npad = NPAD(l);
-                const uint32_t tsrc = tmem_base + (uint32_t)((l & 1) * a.region_cols) + lane_addr;
+                const uint32_t tbase = tmem_base + (uint32_t)((l & 1) * a.region_cols) + lane_addr;
                 warp_wait(&d_ready, dl & 1);
                 ++dl;
                 tcgen05_fence_after();
                 TC_STAMP(30);
                 const float inv = bias_s[bias_off + npad];   // 1 / weight scale of the last layer
-                uint32_t v[16];
-                int c0 = 16 * g;
-                if (c0 < npad) tmem_ld_32x16(tsrc + (uint32_t)c0, v);
-                for (; c0 < npad; c0 += 16 * TC_GROUPS) {
-                    tmem_ld_wait();
-                    if (a.dbg & 8) break;
-                    float x[16];
+                const float *bl = bias_s + bias_off;
+                if (a.group > 0) {
+                    // Transposed accumulator: TMEM lane = output channel (block cb, lane r), column = tile
+                    // row (point).  Group g reduces the columns [g*SEG, (g+1)*SEG) of every channel block,
+                    // 32 columns (one smallest centroid group) at a time: a per-thread max of the raw
+                    // accumulators -- inv > 0, so bias and ReLU are applied to the maxima only.
+                    constexpr int SEG = TC_ROWS / G;              // 32 | 64 | 128 columns per producer group
+                    const int nblk = (npad + 127) / 128;
+                    for (int cb = 0; cb < nblk; ++cb) {
+                        const uint32_t tsrc = tbase + (uint32_t)(cb * 128 + g * SEG);
+                        uint32_t v0[16], v1[16];
+                        tmem_ld_32x16(tsrc, v0);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float t = fmaf(__uint_as_float(v[j]), inv, bias_s[bias_off + c0 + j]);
-                        x[j] = a.relu_last ? fmaxf(t, 0.f) : t;
-                    }
-                    if (c0 + 16 * TC_GROUPS < npad) tmem_ld_32x16(tsrc + (uint32_t)(c0 + 16 * TC_GROUPS), v);
-                    if (a.group > 0) {
-                        // max over the 32 rows of this warp for each of the 16 columns
-                        if (!valid) {
+                        for (int q = 0; q < SEG / 32; ++q) {
+                            tmem_ld_32x16(tsrc + (uint32_t)(32 * q + 16), v1);
+                            tmem_ld_wait();                       // waits for both; v0 is consumed first
+                            float m = __uint_as_float(v0[0]);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) x[j] = -INFINITY;
+                            for (int j = 1; j < 16; ++j) m = fmaxf(m, __uint_as_float(v0[j]));
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v1[j]));
+                            asm volatile("" : "+f"(m));
+                            if (q + 1 < SEG / 32) tmem_ld_32x16(tsrc + (uint32_t)(32 * (q + 1)), v0);
+                            red[(g * (SEG / 32) + q) * 256 + cb * 128 + r] = m;
                         }
-                        int col;
-                        const float m = warp_colmax16(x, lane, col);
-                        if (lane < 16) red[(warp & 3) * 256 + c0 + col] = m;
-                    } else if (valid) {
+                    }
+                    // combine the 32-column maxima that belong to one centroid and write them out
+                    const int wpg = a.group / 32;                 // 32-column segments per centroid: 1, 2 or 4
+                    tcgen05_fence_before();
+                    asm volatile("bar.sync 1, %0;" ::"n"(PROD) : "memory");
+                    const int ngroups = 4 / wpg;
+                    for (int o = tid; o < ngroups * npad; o += PROD) {
+                        const int gi = o / npad, c = o - gi * npad;
+                        const int64_t cen = (tile * TC_ROWS) / a.group + gi;
+                        if (c >= cout_last || cen * a.group >= a.rows) continue;
+                        float m = red[(gi * wpg) * 256 + c];
+                        for (int w = 1; w < wpg; ++w) m = fmaxf(m, red[(gi * wpg + w) * 256 + c]);
+                        a.out[cen * a.ldo + col_off + c] = fmaxf(fmaf(m, inv, bl[c]), 0.f);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(PROD) : "memory");   // red is reused by the next tile
+                } else {
+                    // row-major accumulator: the groups alternate 16-column chunks of the thread's row
+                    const uint32_t tsrc = tbase;
+                    uint32_t v[16];
+                    int c0 = cg;
+                    if (c0 < npad) tmem_ld_32x16(tsrc + (uint32_t)c0, v);
+                    for (; c0 < npad; c0 += KC) {
+                        tmem_ld_wait();
+                        float x[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x[j] = fmaf(__uint_as_float(v[j]), inv, bl[c0 + j]);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) asm volatile("" : "+f"(x[j]));
+                        if (c0 + KC < npad) tmem_ld_32x16(tsrc + (uint32_t)(c0 + KC), v);
+                        if (!valid) continue;
+                        if (a.relu_last) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+                        }
                         float *dst = a.out + grow * a.ldo + col_off + c0;
                         if (c0 + 16 <= cout_last && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -599,21 +696,6 @@ __global__ void __launch_bounds__(SMALL ? 192 : 320, SMALL ? 2 : 1) mlp_tc_kerne
                         }
                     }
                 }
-                if (a.group > 0) {
-                    // combine the per-warp maxima of the warps that share a group and write them out
-                    const int wpg = a.group / 32;                 // row-warps per group: 1, 2 or 4
-                    asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
-                    const int ngroups = 4 / wpg;
-                    for (int o = tid; o < ngroups * npad; o += TC_PROD) {
-                        const int gi = o / npad, c = o - gi * npad;
-                        const int64_t cen = (tile * TC_ROWS) / a.group + gi;
-                        if (c >= cout_last || cen * a.group >= a.rows) continue;
-                        float m = red[(gi * wpg) * 256 + c];
-                        for (int w = 1; w < wpg; ++w) m = fmaxf(m, red[(gi * wpg + w) * 256 + c]);
-                        a.out[cen * a.ldo + col_off + c] = m;
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");   // red aliases a_stage[0]
-                }
                 tcgen05_fence_before();
                 TC_STAMP(31);
             }
@@ -622,7 +704,7 @@ __global__ void __launch_bounds__(SMALL ? 192 : 320, SMALL ? 2 : 1) mlp_tc_kerne
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == TC_PROD / 32) tmem_dealloc_dyn(tmem_base, (uint32_t)a.tmem_cols);
+    if (warp == PROD / 32) tmem_dealloc_dyn(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 // bias -> [npad + 16]: bias, then 1/scale at [npad] and scale at [npad+1].  The weight scale is a power of
@@ -686,7 +768,7 @@ __global__ void pack_tc_kernel(int cin, int cout, int kpad, int npad, int nchunk
 }
 
 struct TcLayout {
-    int nlayers, kpad[CAPTRA_MAX_MLP_LAYERS], npad[CAPTRA_MAX_MLP_LAYERS];
+    int nlayers, kpad[CAPTRA_MAX_MLP_LAYERS], npad[CAPTRA_MAX_MLP_LAYERS], kreal[CAPTRA_MAX_MLP_LAYERS];
     size_t off_w[CAPTRA_MAX_MLP_LAYERS], off_b[CAPTRA_MAX_MLP_LAYERS], total_floats;
     int wstage_bytes, bias_floats, nsplit, last_npad;
     int nstages, region_cols, tmem_cols, target_occ;
@@ -713,9 +795,12 @@ static TcLayout tc_layout_v(const captra_mlp_desc &d, bool f16, bool small) {
     size_t off = 0;
     int cin = d.cin, npmax = 32;
     for (int l = 0; l < d.nlayers; ++l) {
+        // input channels that carry data: the true width of layer 0, then the previous layer's
+        // accumulator columns (its outputs rounded up to the MMA N granularity; the columns past cout
+        // are exact zeros).  The slab padding beyond kreal is never produced nor multiplied.
+        L.kreal[l] = cin;
         L.kpad[l] = round_up(cin, TC_KC);
-        // a non-last layer's accumulator columns are the next layer's K: pad to whole slabs
-        L.npad[l] = round_up(d.cout[l], l < d.nlayers - 1 ? TC_KC : 16);
+        L.npad[l] = round_up(d.cout[l], 16);
         if (L.npad[l] > 256) {
             if (d.nlayers == 1) {   // one wide layer: 256-column chunks over grid.y
                 L.nsplit = ceil_div(L.npad[l], 256);
@@ -725,7 +810,7 @@ static TcLayout tc_layout_v(const captra_mlp_desc &d, bool f16, bool small) {
             }
         }
         npmax = max(npmax, min(L.npad[l], 256));
-        // packed weights of a layer: nslab * 2 planes * 8 chunks * npad * 16 bytes (in floats: /4)
+        // packed weights of a layer: nslab * 2 planes * NCHUNK chunks * npad * 16 bytes (in floats: /4)
         L.off_w[l] = off; off += (size_t)(L.kpad[l] / TC_KC) * 2 * TC_NCHUNK * L.npad[l] * 4;
         const int nb = L.nsplit > 1 ? L.nsplit * (256 + TC_BIAS_PAD) : L.npad[l] + TC_BIAS_PAD;
         L.off_b[l] = off; off += nb;
@@ -739,7 +824,7 @@ static TcLayout tc_layout_v(const captra_mlp_desc &d, bool f16, bool small) {
     L.tmem_cols = d.nlayers > 1 ? 2 * L.region_cols : L.region_cols;
     L.target_occ = 1;
     // LARGE: 4 pipeline stages if they fit in 227 KB, else 2.  SMALL: 2 stages, two CTAs per SM.
-    const size_t fixed = (size_t)L.bias_floats * 4 + 256;
+    const size_t fixed = (size_t)L.bias_floats * 4 + 256 + 4096;   // biases, slack, the grouped epilogue's [4][256] buffer
     const size_t per_stage = (size_t)TC_A_STAGE + L.wstage_bytes;
     const size_t budget = small ? (size_t)(227 * 1024) / 2 - 2048 : (size_t)225 * 1024;
     L.nstages = (!small && fixed + 4 * per_stage <= budget) ? 4 : 2;
@@ -797,12 +882,8 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool
     a.wstage_bytes = L.wstage_bytes; a.bias_floats = L.bias_floats;
     a.region_cols = L.region_cols; a.tmem_cols = L.tmem_cols; a.nst_log2 = L.nstages == 4 ? 2 : 1;
     a.nsplit = L.nsplit; a.last_npad = L.last_npad; a.cout_total = d->cout[d->nlayers - 1];
-    {
-        const int kc = tc_kc(f16, L.small), kmma = f16 ? 16 : 8;
-        a.cin0 = d->cin;
-        const int rem = d->cin - (L.kpad[0] / kc - 1) * kc;     // channels in layer 0's last slab
-        a.klast0 = ceil_div(rem, kmma);
-    }
+    for (int l = 0; l < d->nlayers; ++l) a.kreal[l] = L.kreal[l];
+    a.cin0 = d->cin;
     { const char *e = getenv("CAPTRA_TC_DBG"); a.dbg = e ? atoi(e) : 0; }
     *smem = L.smem_bytes;
     return CAPTRA_OK;
@@ -814,9 +895,20 @@ static int tc_launch_t(TcArgs &a, size_t smem, cudaStream_t stream) {
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
+    a.tpose = a.group > 0 ? 1 : 0;
+    if (a.tpose) {
+        // the transposed last layer accumulates 128-channel blocks of 128 columns (points) each
+        // (a wide single layer split over grid.y: every CTA owns at most 256 channels = two blocks)
+        const int need = a.nsplit > 1 ? 256 : ceil_div(a.npad[a.nlayers - 1], 128) * 128;
+        if (a.region_cols < need) {
+            a.region_cols = need;     // 128 or 256: already a power of two
+            a.tmem_cols = a.nlayers > 1 ? 2 * need : need;
+        }
+        CAPTRA_REQUIRE(a.tmem_cols <= (SMALL ? 256 : 512), "mlp(tc): grouped max does not fit the tensor memory");
+    }
     const int64_t slots = (int64_t)max(1, sm_count() / a.nsplit) * (SMALL ? 2 : 1);
     const int gx = (int)(a.ntiles < slots ? a.ntiles : slots);
-    kern<<<dim3(gx, a.nsplit), SMALL ? 192 : 320, smem, stream>>>(a);
+    kern<<<dim3(gx, a.nsplit), tc_threads(F16, SMALL), smem, stream>>>(a);
     CAPTRA_CHECK_LAUNCH("mlp_tc");
     return CAPTRA_OK;
 }
@@ -855,6 +947,16 @@ static int tc_point_mlp_ex(int64_t rows, const float *segA, int64_t ldA, int ca,
     a.out = y; a.ldo = ldy; a.col_off = col_off;
     a.segA = segA; a.ldA = ldA; a.ca = ca; a.segB = segB; a.ldB = ldB; a.cb = cb; a.bcast = bcast;
     a.in_scale = in_scale; a.in_shift = in_shift; a.rows_per_cloud = rows_per_cloud;
+    if (in_scale) {
+        // a tile must not straddle two clouds: the kernel stages one cloud's scale/shift rows per tile
+        CAPTRA_REQUIRE(rows_per_cloud % TC_ROWS == 0, "point_mlp_affine: rows_per_cloud must be a multiple of %d (got %d)", TC_ROWS, rows_per_cloud);
+        CAPTRA_REQUIRE(cb == 0 && segB == nullptr, "point_mlp_affine: single input segment only");
+        const int pad = round_up(ca, 16);
+        const size_t extra = (size_t)2 * pad * sizeof(float);
+        const size_t budget = a.small ? (size_t)(227 * 1024) / 2 - 2048 : (size_t)225 * 1024;
+        CAPTRA_REQUIRE(smem + extra <= budget, "point_mlp_affine: %d input channels do not fit the shared-memory budget", ca);
+        a.aff_pad = pad; smem += extra;
+    }
     return tc_launch<1>(a, smem, stream);
 }
 

@@ -39,6 +39,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
 
+// all 32 lanes poll; the loop condition is a vote, so the compiler sees warp-uniform control flow and
+// keeps the values that live across the wait (descriptors, counters) in uniform registers
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {}
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- proxies / fences ----------------------------------------------------------------------
 // generic-proxy st.shared must be made visible to the async proxy (UMMA / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -1,6 +1,6 @@
-"""Timing probes for the fused tcgen05 MLP kernel: runs the two dominant SA scales of cfg2 with the
-CAPTRA_TC_DBG knobs (1 no A stores, 2 no W copies, 4 no MMAs, 8 no last epilogue; results are
-garbage, only the time matters) to see which role bounds the tile time."""
+"""Timing probe for the fused tcgen05 MLP kernel: the SA scales and dense-row shapes of cfg2, each
+timed alone (PROBE_IMPL = 1 | 2; PROBE_STAMPS=1 prints the clock64 phase stamps of a build made with
+CAPTRA_TC_DBG bit 32); PROBE_DBG=0,2,4,... times the knock-out knobs."""
 import os
 import sys
 import time
@@ -23,7 +23,7 @@ def mk(cin, couts):
         ws.append((torch.randn(c, last, generator=gen) / last ** 0.5).to(dev))
         bs.append((0.1 * torch.randn(c, generator=gen)).to(dev))
         last = c
-    return PackedMLP(ws, bs, impl=int(os.environ.get('PROBE_IMPL', '1')))
+    return PackedMLP(ws, bs, impl=int(os.environ.get('PROBE_IMPL', '2')))
 
 
 cases = []
@@ -38,38 +38,64 @@ cases.append(("sa2 K=128 323->128-196-256", mk(323, [128, 196, 256]), c1, c2, f2
 i3 = fused_ops.ball_query_multi([0.2], [64], c1, c2)[0]
 cases.append(("sa2 K=64 323->128-128-256", mk(323, [128, 128, 256]), c1, c2, f2, i3))
 
+for r, k in ((0.1, 64), (0.05, 32)):
+    ii = fused_ops.ball_query_multi([r], [k], pts, c1)[0]
+    cases.append(("sa1 K=%d 6->%s" % (k, "32-32-64" if k == 32 else "64-64-128"), mk(6, [32, 32, 64] if k == 32 else [64, 64, 128]), pts, c1, pts.contiguous(), ii))
+
+
+def timeit(fn, n=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / n
+
+
+DBGS = [int(v) for v in os.environ.get("PROBE_DBG", "0").split(",")]
 for name, mlp, xyz, ctr, feats, idx in cases:
     out = torch.empty(B, ctr.shape[1], mlp.cout, device=dev)
-    for dbg in (0,):
+    rows = B * ctr.shape[1] * idx.shape[2]
+    fl = 2.0 * rows * sum(a * b for a, b in zip([mlp.cin] + mlp.couts[:-1], mlp.couts))
+    for dbg in DBGS:   # CAPTRA_TC_DBG knobs: results are garbage, only the time matters
         os.environ["CAPTRA_TC_DBG"] = str(dbg)
-        for _ in range(2):
-            mlp.sa_max(xyz, ctr, feats, idx, out)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            mlp.sa_max(xyz, ctr, feats, idx, out)
-        e1.record()
-        torch.cuda.synchronize()
-        print("%-30s dbg=%2d  %8.1f us" % (name, dbg, 1e3 * e0.elapsed_time(e1) / 5))
+        us = timeit(lambda: mlp.sa_max(xyz, ctr, feats, idx, out))
+        print("%-30s dbg=%2d %8.1f us  %6.1f TFLOP/s (algorithmic)" % (name, dbg, us, fl / us * 1e-6))
 os.environ["CAPTRA_TC_DBG"] = "0"
 
-# phase timestamps of CTA 0's first tiles (dbg bit 32)
-import ctypes
-from captra_b200 import _lib
-L = _lib.load()
-for name, mlp, xyz, ctr, feats, idx in cases:
-    out = torch.empty(B, ctr.shape[1], mlp.cout, device=dev)
-    for dbg in (32,):
+# dense rows: the RotationRegressor head layers (GroupNorm affine on load) and fp1 + conv1
+R = B * 4096
+x512 = torch.randn(R, 512, generator=gen).to(dev)
+sc, sh = torch.rand(B, 512, generator=gen).to(dev) + 0.5, torch.randn(B, 512, generator=gen).to(dev)
+for cin, cout in ((512, 512), (512, 256)):
+    m = PackedMLP([(torch.randn(cout, cin, generator=gen) / cin ** 0.5).to(dev)], [torch.zeros(cout).to(dev)], relu_last=False,
+                  impl=int(os.environ.get('PROBE_IMPL', '2')))
+    y = torch.empty(R, cout, device=dev)
+    us = timeit(lambda: m.rows_affine(x512, sc, sh, 4096, out=y))
+    print("%-30s %8.1f us  %6.1f TFLOP/s" % ("head %d->%d affine" % (cin, cout), us, 2.0 * R * cin * cout / us * 1e-6))
+x128 = torch.randn(R, 128, generator=gen).to(dev)
+for couts in ([512], [128, 128, 128]):
+    m = mk(128, couts)
+    us = timeit(lambda: m.rows(x128))
+    fl = 2.0 * R * sum(a * b for a, b in zip([128] + couts[:-1], couts))
+    print("%-30s %8.1f us  %6.1f TFLOP/s" % ("rows 128->%s" % "-".join(map(str, couts)), us, fl / us * 1e-6))
+
+if os.environ.get("PROBE_STAMPS"):
+    import ctypes
+    from captra_b200 import _lib
+    L = _lib.load()
+    for name, mlp, xyz, ctr, feats, idx in cases:
+        out = torch.empty(B, ctr.shape[1], mlp.cout, device=dev)
         buf = (ctypes.c_longlong * 512)()
         L.captra_debug_tc_timestamps(buf, 255)
-        os.environ["CAPTRA_TC_DBG"] = str(dbg)
+        os.environ["CAPTRA_TC_DBG"] = "32"
         mlp.sa_max(xyz, ctr, feats, idx, out)
+        os.environ["CAPTRA_TC_DBG"] = "0"
         n = L.captra_debug_tc_timestamps(buf, 255)
         ts = [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
-        print(name, "dbg", dbg, "stamps", n)
-        line = []
-        for i in range(1, min(n, 19)):
-            line.append("%d->%d:%d" % (ts[i - 1][1], ts[i][1], ts[i][0] - ts[i - 1][0]))
-        print("  " + "  ".join(line))
-os.environ["CAPTRA_TC_DBG"] = "0"
+        print(name, "stamps", n)
+        print("  " + "  ".join("%d->%d:%d" % (ts[i - 1][1], ts[i][1], ts[i][0] - ts[i - 1][0]) for i in range(1, min(n, 19))))
