@@ -9,7 +9,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcaptra_ops.so")
+LIB_PATH = os.environ.get("CAPTRA_LIB_PATH") or os.path.join(_PKG, "libcaptra_ops.so")   # override: A/B kernel variants
 
 _lib = None
 

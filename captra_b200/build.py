@@ -14,8 +14,11 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(PKG, "_build")
-LIB = os.path.join(PKG, "libcaptra_ops.so")
+# A/B experiments: CAPTRA_EXTRA_NVCC_FLAGS="-DX" CAPTRA_LIB_OUT=captra_b200/libcaptra_ops_x.so python -m captra_b200.build
+# builds a variant beside the product library (select it at run time with CAPTRA_LIB_PATH).
+_VARIANT = os.environ.get("CAPTRA_LIB_OUT")
+OBJ = os.path.join(PKG, "_build" if not _VARIANT else "_build_" + os.path.basename(_VARIANT).replace(".so", ""))
+LIB = os.path.abspath(_VARIANT) if _VARIANT else os.path.join(PKG, "libcaptra_ops.so")
 
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = [
@@ -24,7 +27,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + os.environ.get("CAPTRA_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

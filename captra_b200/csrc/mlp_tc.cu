@@ -137,6 +137,10 @@ __host__ __device__ constexpr int tc_kc(bool f16, bool small) { return (f16 ? 64
 __host__ __device__ constexpr int tc_groups(bool f16, bool small) { return tc_kc(f16, small) / 16; }
 __host__ __device__ constexpr int tc_threads(bool f16, bool small) { return 128 * tc_groups(f16, small) + 64; }
 
+// Registers: the 64 K registers of an SM are split over its four sub-partitions (16 K each) and a CTA's warps are
+// dealt out round-robin, so the per-thread budget follows the sub-partition with the most warps: 18 warps (LARGE
+// fp16x3) or 2 x 10 (SMALL fp16x3) -> 5 warps -> 96 registers; 10 or 2 x 6 warps (3xTF32) -> 3 warps -> 168.
+// __launch_bounds__ makes ptxas apply exactly that (a larger __maxnreg__ fails at launch).
 struct TcArgs {
     int nlayers, relu_last, cout_last;
     int kpad[CAPTRA_MAX_MLP_LAYERS], npad[CAPTRA_MAX_MLP_LAYERS];
@@ -249,7 +253,7 @@ struct TcPiece {
 // or 2 (3xTF32) producer groups, one CTA per SM.  SMALL (every layer <= 128 columns: the sa1 scales,
 // fp1): 4-chunk slabs, G = 2 / 1, 64 KB and 256 TMEM columns per CTA so TWO CTAs share an SM and one
 // tile's epilogue overlaps the other's MMAs.
-template <int MODE, bool F16, bool SMALL>  // MODE 0: SA gather loader, 1: dense-row loader; the last epilogue is chosen by a.group
+template <int MODE, bool F16, bool SMALL, int NSTL2>  // MODE 0: SA gather loader, 1: dense-row loader; 2^NSTL2 pipeline stages; the last epilogue is chosen by a.group
 __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_kernel(const TcArgs a) {
     constexpr int G = tc_groups(F16, SMALL);
     constexpr int PROD = 128 * G;                  // producer / epilogue threads (warps 0 .. 4G-1)
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
     __shared__ uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], d_ready;
     __shared__ uint32_t tmem_base_s;
 
-    const uint32_t nst_log2 = (uint32_t)a.nst_log2, NST = 1u << nst_log2;
+    constexpr uint32_t nst_log2 = NSTL2, NST = 1u << NSTL2;   // compile-time: stage addresses and parities fold into immediates
     uint8_t *a_stage = smem_raw;                                          // NST x A_STAGE
     uint8_t *w_stage = a_stage + (size_t)NST * A_STAGE;                   // NST x wstage_bytes
     float *bias_s = reinterpret_cast<float *>(w_stage + (size_t)NST * a.wstage_bytes);
@@ -414,8 +418,8 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
         }
     } else {
         // ===================== producer / epilogue threads =====================
-        const int r = tid & 127;              // tile row == TMEM lane
-        const int g = tid >> 7;               // producer group == piece of every slab
+        const int r = tid & 127;              // tile row == TMEM lane (layers > 0 and the epilogue)
+        const int g = tid >> 7;               // producer group == piece of every slab (layers > 0)
         const int cg = 16 * g;                // first channel of this thread's piece within a slab
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         // this thread's 16 bytes of chunk 0 of its piece in stage 0 (hi plane)
@@ -424,6 +428,58 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
         uint32_t dl = 0;
         float amax = 0.f;                     // largest |operand| this thread converted to fp16
         int aff_cloud = -1;                   // cloud whose scale/shift rows sit in aff_s
+
+        // ---- layer-0 loader geometry.  Layer 0 has no tie to the TMEM lanes, so its rows are dealt out
+        // for COALESCED global reads: a warp owns ROWS_W consecutive tile rows; one load instruction
+        // covers RPI rows x LPR lanes x 32 bytes (8 fp32 channels = one "unit"), i.e. 128 contiguous
+        // bytes per row (LDG.256: 8 cache lines per instruction instead of the 32 a thread-per-row
+        // gather touches), and a lane keeps two units per slab.  A unit is exactly one 16-byte fp16
+        // operand chunk (two tf32 chunks), and the 8 lanes of a quarter warp hold 8 consecutive rows of
+        // the same chunk, so the operand stores stay 16-byte wide and bank-conflict free.
+        constexpr int UPR = KC / 8;                     // units per row per slab: 8 | 4 | 4 | 2
+        constexpr int LPR = UPR < 4 ? UPR : 4;          // lanes sharing a row in one instruction
+        constexpr int RPI = 32 / LPR;                   // rows per instruction
+        constexpr int ROWS_W = TC_ROWS / (4 * G);       // rows owned by a warp
+        constexpr int RS = ROWS_W / RPI;                // row sets per warp
+        constexpr int US = UPR / LPR;                   // unit sets per row
+        static_assert(RS * US == 2 && (RS == 1 || US == 1), "two 32-byte units per lane per slab");
+        const int lrow = lane % RPI, lcq = lane / RPI;
+        auto unit_row = [&](int u) { return warp * ROWS_W + (RS == 2 ? u * RPI : 0) + lrow; };   // tile row of unit u
+        auto unit_idx = [&](int u) { return lcq + (US == 2 ? u * LPR : 0); };                     // unit within the slab
+        const int glog2 = a.group > 0 ? __ffs(a.group) - 1 : 0;
+
+        struct RowMeta {                      // one tile row of the layer-0 loader
+            bool valid;
+            const float *pa, *pb;             // SA: feature row (or null); dense: rows of the two input segments
+            float q[3];                       // SA: point coordinates (the centroid is subtracted where they are used)
+        };
+        // SA: a tile starts with two dependent L2 round trips (neighbour index -> coordinates / feature
+        // row).  They are taken off the critical path with L1 prefetches issued while the PREVIOUS tile
+        // runs (index line after layer 0, the rows it points to before the last epilogue); nothing is
+        // carried in registers across the tile boundary.
+        auto prefetch_l1 = [](const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); };
+        auto meta_prefetch_idx = [&](int64_t tile) {
+            if (MODE != 0 || lcq != 0) return;
+#pragma unroll
+            for (int ri = 0; ri < RS; ++ri) {
+                const int64_t lg = tile * TC_ROWS + warp * ROWS_W + ri * RPI + lrow;
+                if (lg < a.rows && (lrow & 7) == 0) prefetch_l1(a.idx + lg);      // 8 rows = one 32-byte sector
+            }
+        };
+        auto meta_prefetch_rows = [&](int64_t tile) {
+            if (MODE != 0 || lcq != 0) return;
+#pragma unroll
+            for (int ri = 0; ri < RS; ++ri) {
+                const int64_t lg = tile * TC_ROWS + warp * ROWS_W + ri * RPI + lrow;
+                if (lg >= a.rows) continue;
+                const uint32_t cen = (uint32_t)(lg >> glog2);                      // rows / group < 2^31 (host check)
+                const int64_t pnt = (int64_t)(cen / (uint32_t)a.s) * a.n + __ldg(a.idx + lg);
+                prefetch_l1(a.xyz + pnt * 3);
+                prefetch_l1(a.xyz + pnt * 3 + 2);
+                if (a.feats) prefetch_l1(a.feats + pnt * a.cfeat);
+                if (lrow == 0) prefetch_l1(a.new_xyz + (int64_t)cen * 3 + 2);
+            }
+        };
 
         auto warp_wait = [&](uint64_t *bar, uint32_t parity) {   // one lane polls, the warp follows
             if (lane == 0) mbar_wait(bar, parity);
@@ -468,27 +524,65 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 *reinterpret_cast<uint4 *>(lo + q * TC_CHUNK_BYTES) = make_uint4(p.lo[4 * q], p.lo[4 * q + 1], p.lo[4 * q + 2], p.lo[4 * q + 3]);
             }
         };
+        // one layer-0 unit (8 signed fp32 values) -> operand words: 4 + 4 packed fp16 pairs, or 8 + 8 tf32
+        auto convert_unit = [&](const float (&x)[8], uint32_t (&hi)[F16 ? 4 : 8], uint32_t (&lo)[F16 ? 4 : 8]) {
+            if (F16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    split2_f16<false>(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+                    amax = fmaxf(fmaxf(amax, fabsf(x[2 * j])), fabsf(x[2 * j + 1]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float h, l;
+                    split_tf32(x[j], h, l);
+                    hi[j] = __float_as_uint(h); lo[j] = __float_as_uint(l);
+                }
+            }
+        };
+        auto store_unit = [&](uint32_t i, int row, int uq, const uint32_t (&hi)[F16 ? 4 : 8], const uint32_t (&lo)[F16 ? 4 : 8]) {
+            uint8_t *ph = a_stage + (size_t)(i & (NST - 1)) * A_STAGE + (size_t)(F16 ? uq : 2 * uq) * TC_CHUNK_BYTES + row * 16;
+            uint8_t *pl = ph + A_PLANE;
+#pragma unroll
+            for (int q = 0; q < (F16 ? 1 : 2); ++q) {
+                *reinterpret_cast<uint4 *>(ph + q * TC_CHUNK_BYTES) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                *reinterpret_cast<uint4 *>(pl + q * TC_CHUNK_BYTES) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            }
+        };
 
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            const int64_t grow = tile * TC_ROWS + r;
+            const int64_t grow = tile * TC_ROWS + r;     // this thread's row in layers > 0 and the epilogue
             const bool valid = grow < a.rows;
+            const int64_t tile_next = tile + gridDim.x;
             TC_STAMP(0);
-            // ---- per-row metadata
-            const float *frow = nullptr;         // SA: feature row of the gathered point
-            float px = 0.f, py = 0.f, pz = 0.f;  // SA: point - centroid
-            const float *arow = nullptr, *brow = nullptr;
-            if (valid) {
+            // ---- layer-0 row metadata
+            RowMeta meta[RS];
+            float cq[3] = {0.f, 0.f, 0.f};   // SA: the centroid of this warp's rows (ROWS_W <= 32 <= group: one centroid per warp and tile)
+            if (MODE == 0) {
+                const int64_t lg0 = tile * TC_ROWS + warp * ROWS_W;
+                if (lg0 < a.rows) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) cq[j] = __ldg(a.new_xyz + (lg0 >> glog2) * 3 + j);
+                }
+            }
+#pragma unroll
+            for (int ri = 0; ri < RS; ++ri) {
+                const int64_t lg = tile * TC_ROWS + warp * ROWS_W + ri * RPI + lrow;
+                meta[ri].valid = lg < a.rows;
+                meta[ri].pa = meta[ri].pb = nullptr;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) meta[ri].q[j] = 0.f;
+                if (!meta[ri].valid) continue;
                 if (MODE == 0) {
-                    const int64_t cen = grow / a.group;
-                    const int64_t b = cen / a.s;
-                    const int64_t p = b * a.n + __ldg(a.idx + grow);
-                    frow = a.feats ? a.feats + p * a.cfeat : nullptr;
-                    px = __fsub_rn(__ldg(a.xyz + p * 3 + 0), __ldg(a.new_xyz + cen * 3 + 0));
-                    py = __fsub_rn(__ldg(a.xyz + p * 3 + 1), __ldg(a.new_xyz + cen * 3 + 1));
-                    pz = __fsub_rn(__ldg(a.xyz + p * 3 + 2), __ldg(a.new_xyz + cen * 3 + 2));
+                    const uint32_t cen = (uint32_t)(lg >> glog2);
+                    const int64_t pnt = (int64_t)(cen / (uint32_t)a.s) * a.n + __ldg(a.idx + lg);
+                    meta[ri].pa = a.feats ? a.feats + pnt * a.cfeat : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) meta[ri].q[j] = __ldg(a.xyz + pnt * 3 + j);
                 } else {
-                    arow = a.segA ? a.segA + grow * a.ldA : nullptr;
-                    brow = a.segB ? a.segB + (a.bcast ? grow / a.bcast : grow) * a.ldB : nullptr;
+                    meta[ri].pa = a.segA ? a.segA + lg * a.ldA : nullptr;
+                    meta[ri].pb = a.segB ? a.segB + (a.bcast ? lg / a.bcast : lg) * a.ldB : nullptr;
                 }
             }
             if (MODE == 1 && a.in_scale) {
@@ -505,37 +599,42 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                     aff_cloud = cloud;
                 }
             }
-            auto load_piece = [&](int c0, float (&x)[16]) {            // 16 consecutive layer-0 channels from c0
+            // 8 consecutive layer-0 channels from c0 of one row
+            auto load_unit = [&](const RowMeta &m, int c0, float (&x)[8]) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) x[j] = 0.f;
-                if (!valid || c0 >= a.cin0 || (a.dbg & 65)) return;   // padding rows / channels (probes: no gather)
-                // segment base pointers moved to channel c0, so every element is base + constant
-                const float *pa = MODE == 0 ? frow + c0 : arow + c0;
-                const float *pb = MODE == 0 ? nullptr : brow + (c0 - a.ca);
-                const int na = (MODE == 0 ? a.cfeat : a.ca) - c0;     // channels of the leading segment left from c0
-                const int nb = MODE == 0 ? 3 : a.cb;                  // SA: dx, dy, dz follow the features
-                const float *vp = nullptr;                            // 16 contiguous, 16-byte aligned floats?
-                if (na >= 16) vp = pa;
-                else if (MODE == 1 && na <= 0 && na + nb >= 16) vp = pb;
-                if (vp && (reinterpret_cast<uintptr_t>(vp) & 15) == 0) {
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+                if (!m.valid || c0 >= a.cin0 || (a.dbg & 65)) return;   // padding rows / channels (probes: no gather)
+                const int ca = MODE == 0 ? a.cfeat : a.ca;            // width of the leading segment
+                const int na = ca - c0;                               // its channels left from c0
+                const float *vp = nullptr;                            // 8 contiguous floats?
+                if (na >= 8) vp = m.pa + c0;
+                else if (MODE == 1 && na <= 0 && a.cb + na >= 8) vp = m.pb - na;
+                const uintptr_t al = reinterpret_cast<uintptr_t>(vp);
+                if (vp && (al & 31) == 0) {
+                    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7])
+                                 : "l"(vp));
+                } else if (vp && (al & 15) == 0) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const float4 t = __ldg(reinterpret_cast<const float4 *>(vp) + q);
                         x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (j < na) x[j] = __ldg(pa + j);
-                        else if (j < na + nb) x[j] = MODE == 0 ? (j == na ? px : (j == na + 1 ? py : pz)) : __ldg(pb + j);
+                    for (int j = 0; j < 8; ++j) {
+                        const int t = j - na;                         // channel index within the trailing segment
+                        if (t < 0) x[j] = __ldg(m.pa + c0 + j);
+                        else if (MODE == 0) x[j] = t == 0 ? __fsub_rn(m.q[0], cq[0]) : (t == 1 ? __fsub_rn(m.q[1], cq[1]) : (t == 2 ? __fsub_rn(m.q[2], cq[2]) : 0.f));
+                        else if (t < a.cb) x[j] = __ldg(m.pb + t);
                     }
                 }
             };
-            // GroupNorm + ReLU of the producer layer, applied to a loaded piece (dense mode)
-            auto affine_piece = [&](int c0, float (&x)[16]) {
-                if (MODE != 1 || !a.in_scale || !valid || c0 >= a.cin0) return;
+            // GroupNorm + ReLU of the producer layer, applied to a loaded unit (dense mode)
+            auto affine_unit = [&](const RowMeta &m, int c0, float (&x)[8]) {
+                if (MODE != 1 || !a.in_scale || !m.valid || c0 >= a.cin0) return;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < 2; ++q) {
                     const float4 sc = *reinterpret_cast<const float4 *>(aff_s + c0 + 4 * q);
                     const float4 sh = *reinterpret_cast<const float4 *>(aff_s + a.aff_pad + c0 + 4 * q);
                     x[4 * q] = fmaxf(fmaf(x[4 * q], sc.x, sh.x), 0.f);
@@ -545,33 +644,51 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 }
             };
             TC_STAMP(1);
-            // ---------------- layer 0: piece g of every slab, gathered two slabs ahead ----------------
+            // ---------------- layer 0: coalesced gather, two slabs ahead ----------------
             {
-                const int nslab = a.kpad[0] / KC, kreal = a.kreal[0];
-                float b0[16], b1[16];
-                load_piece(cg, b0);
-                if (nslab > 1) load_piece(KC + cg, b1);
-                auto step = [&](int s, float (&buf)[16]) {   // buf holds slab s and is refilled with slab s + 2
-                    const int c0 = s * KC + cg;
-                    const bool active = c0 < kreal && !(a.dbg & 1);   // else: pure padding, the MMA thread skips these k-steps
+                const int nslab = a.kpad[0] / KC;
+                const int kstore = (a.kreal[0] + KMMA - 1) / KMMA * KMMA;   // channels the MMA k-steps read
+                // prefetch distance: two slabs where the register budget allows (3xTF32 LARGE: 168), else one (96)
+#ifdef CAPTRA_TC_PF2      // A/B build knob (scripts/ab_build.sh)
+                constexpr int PF = SMALL ? 1 : 2;
+#else
+                constexpr int PF = (SMALL || F16) ? 1 : 2;
+#endif
+                float b0[2][8], b1[PF == 2 ? 2 : 1][8];
+                auto load_slab = [&](int s, float (&buf)[2][8]) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) load_unit(meta[RS == 2 ? u : 0], s * KC + 8 * unit_idx(u), buf[u]);
+                };
+                auto step = [&](int s, float (&buf)[2][8]) {   // buf holds slab s and is refilled with slab s + PF
                     acquire(it);
-                    if (active) {
-                        TcPiece<F16> p;
-                        affine_piece(c0, buf);
-                        convert(buf, std::false_type{}, p);
-                        store_piece(it, p);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int c0 = s * KC + 8 * unit_idx(u);
+                        if (c0 < kstore && !(a.dbg & 1)) {        // else: pure padding, the MMA thread skips these k-steps
+                            uint32_t hi[F16 ? 4 : 8], lo[F16 ? 4 : 8];
+                            affine_unit(meta[RS == 2 ? u : 0], c0, buf[u]);
+                            convert_unit(buf[u], hi, lo);
+                            store_unit(it, unit_row(u), unit_idx(u), hi, lo);
+                        }
                     }
                     release(it);
                     // refill only now: the proxy fence in release() waits for the thread's outstanding
                     // loads, which would put the L2 latency of the prefetch on every slab's critical path
-                    if (s + 2 < nslab) load_piece(c0 + 2 * KC, buf);
+                    if (s + PF < nslab) load_slab(s + PF, buf);
                     ++it;
                 };
-                for (int s = 0; s < nslab; s += 2) {
-                    step(s, b0);
-                    if (s + 1 < nslab) step(s + 1, b1);
+                load_slab(0, b0);
+                if constexpr (PF == 2) {
+                    if (nslab > 1) load_slab(1, b1);
+                    for (int s = 0; s < nslab; s += 2) {
+                        step(s, b0);
+                        if (s + 1 < nslab) step(s + 1, b1);
+                    }
+                } else {
+                    for (int s = 0; s < nslab; ++s) step(s, b0);
                 }
             }
+            if (tile_next < a.ntiles) meta_prefetch_idx(tile_next);
             TC_STAMP(2);
             // ---------------- layers 1..L-1: previous accumulator -> next operand ----------------
             int bias_off = 0;
@@ -615,6 +732,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 bias_off += NPAD(l - 1) + TC_BIAS_PAD;
                 TC_STAMP(20 + l);
             }
+            if (tile_next < a.ntiles) meta_prefetch_rows(tile_next);
             // ---------------- last epilogue ----------------
             {
                 const int l = a.nlayers - 1;
@@ -889,9 +1007,9 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool
     return CAPTRA_OK;
 }
 
-template <int MODE, bool F16, bool SMALL>
+template <int MODE, bool F16, bool SMALL, int NSTL2>
 static int tc_launch_t(TcArgs &a, size_t smem, cudaStream_t stream) {
-    auto kern = mlp_tc_kernel<MODE, F16, SMALL>;
+    auto kern = mlp_tc_kernel<MODE, F16, SMALL, NSTL2>;
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
@@ -914,8 +1032,9 @@ static int tc_launch_t(TcArgs &a, size_t smem, cudaStream_t stream) {
 }
 template <int MODE>
 static int tc_launch(TcArgs &a, size_t smem, cudaStream_t stream) {
-    if (a.small) return a.f16 ? tc_launch_t<MODE, true, true>(a, smem, stream) : tc_launch_t<MODE, false, true>(a, smem, stream);
-    return a.f16 ? tc_launch_t<MODE, true, false>(a, smem, stream) : tc_launch_t<MODE, false, false>(a, smem, stream);
+    if (a.small) return a.f16 ? tc_launch_t<MODE, true, true, 1>(a, smem, stream) : tc_launch_t<MODE, false, true, 1>(a, smem, stream);
+    if (a.nst_log2 == 2) return a.f16 ? tc_launch_t<MODE, true, false, 2>(a, smem, stream) : tc_launch_t<MODE, false, false, 2>(a, smem, stream);
+    return a.f16 ? tc_launch_t<MODE, true, false, 1>(a, smem, stream) : tc_launch_t<MODE, false, false, 1>(a, smem, stream);
 }
 
 int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const float *new_xyz,
@@ -923,6 +1042,7 @@ int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const
                   float *out, int64_t ldo, int col_off, bool f16, cudaStream_t stream) {
     CAPTRA_REQUIRE(k == 32 || k == 64 || k == 128, "sa_mlp_max(tc): nsample must be 32, 64 or 128 (got %d)", k);
     CAPTRA_REQUIRE(d->relu_last, "sa_mlp_max(tc): the max epilogue needs a ReLU after the last layer");
+    CAPTRA_REQUIRE((int64_t)b * s < 2147483647LL, "sa_mlp_max(tc): too many centroids (b * s = %lld)", (long long)b * s);
     TcArgs a{};
     size_t smem;
     int rc = tc_fill(a, d, packed, f16, &smem);

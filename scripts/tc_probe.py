@@ -57,16 +57,21 @@ def timeit(fn, n=5):
 
 
 DBGS = [int(v) for v in os.environ.get("PROBE_DBG", "0").split(",")]
+if os.environ.get("PROBE_CASES"):   # e.g. PROBE_CASES=0,1 keeps only those SA cases (ncu captures)
+    cases = [cases[int(i)] for i in os.environ["PROBE_CASES"].split(",")]
+N_TIMED = int(os.environ.get("PROBE_N", "5"))
 for name, mlp, xyz, ctr, feats, idx in cases:
     out = torch.empty(B, ctr.shape[1], mlp.cout, device=dev)
     rows = B * ctr.shape[1] * idx.shape[2]
     fl = 2.0 * rows * sum(a * b for a, b in zip([mlp.cin] + mlp.couts[:-1], mlp.couts))
     for dbg in DBGS:   # CAPTRA_TC_DBG knobs: results are garbage, only the time matters
         os.environ["CAPTRA_TC_DBG"] = str(dbg)
-        us = timeit(lambda: mlp.sa_max(xyz, ctr, feats, idx, out))
+        us = timeit(lambda: mlp.sa_max(xyz, ctr, feats, idx, out), N_TIMED)
         print("%-30s dbg=%2d %8.1f us  %6.1f TFLOP/s (algorithmic)" % (name, dbg, us, fl / us * 1e-6))
 os.environ["CAPTRA_TC_DBG"] = "0"
 
+if os.environ.get("PROBE_DENSE", "1") == "0":
+    sys.exit(0)
 # dense rows: the RotationRegressor head layers (GroupNorm affine on load) and fp1 + conv1
 R = B * 4096
 x512 = torch.randn(R, 512, generator=gen).to(dev)
