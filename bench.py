@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="clouds per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--dump-kernels", default=None, help="write the full per-launch table of the profiled pass (JSON) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
@@ -381,6 +382,9 @@ def main():
             k["hbm_frac"] = k["gbs"] / pk["hbm"]
             k["share_of_step"] = k["ms_per_step"] / step_avg_ms
         kernels.sort(key=lambda k: -k["ms_per_step"])
+        if args.dump_kernels:
+            with open(args.dump_kernels, "w") as f:
+                json.dump({"ms_per_step": step_avg_ms, "captra_ms_per_step": sum(k["ms_per_step"] for k in kernels), "kernels": kernels}, f, indent=1)
         top = kernels[0]
         tname = _parse(top["tag"])[0]
         if tname in ("sa_mlp_max", "point_mlp"):

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
     static_assert(KC == 16 * G && KSTEPS == NCHUNK / 2, "one 16-channel piece per producer group");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], d_ready;
+    __shared__ uint64_t meta_full[2], meta_empty[2];   // SA: per-tile row metadata ring (written by the TMA warp)
     __shared__ uint32_t tmem_base_s;
 
     constexpr uint32_t nst_log2 = NSTL2, NST = 1u << NSTL2;   // compile-time: stage addresses and parities fold into immediates
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
     uint8_t *w_stage = a_stage + (size_t)NST * A_STAGE;                   // NST x wstage_bytes
     float *bias_s = reinterpret_cast<float *>(w_stage + (size_t)NST * a.wstage_bytes);
     float *aff_s = bias_s + a.bias_floats;                                // [2][aff_pad] when a.aff_pad > 0
-    float *red = aff_s + 2 * a.aff_pad;                                   // [4][256] partial maxima of the grouped epilogue (also the slack the
+    float4 *meta_s = reinterpret_cast<float4 *>(aff_s + 2 * a.aff_pad);   // [2 tiles][128 rows][2]: {point, dx, dy, dz}, {first 4 features}
+    float *red = reinterpret_cast<float *>(meta_s + 2 * TC_ROWS * 2);     // [4][256] partial maxima of the grouped epilogue (also the slack the
                                                                           // transposed last layer's 128-row weight reads may run into)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
     if (tid == 0) {
         for (uint32_t i = 0; i < NST; ++i) { mbar_init(&full[i], 4 * G + 1); mbar_init(&empty[i], 1); }
         mbar_init(&d_ready, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&meta_full[i], 1); mbar_init(&meta_empty[i], 4 * G); }
         fence_mbar_init();
     }
     {   // biases of all layers -> smem
@@ -394,9 +397,66 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
             }
         }
     } else if (warp_u == PROD / 32 + 1) {
-        // ===================== weight producer (bulk-copy TMA) =====================
-        uint32_t it = 0;
-        for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        // ===================== weight producer (bulk-copy TMA) + SA row metadata =====================
+        // The weight copies need one elected lane and are never on the critical path, so this warp also
+        // resolves the SA gather's dependent loads for the NEXT tile -- neighbour index -> point ->
+        // coordinates (and, for layer-0 inputs of <= 8 channels, the features themselves) -- spread over
+        // the first three slabs of the current tile, and leaves {point, dx, dy, dz | f0..f3} per row in a
+        // two-tile shared-memory ring.  The producers then start a tile with shared-memory reads instead
+        // of two L2 round trips (1300 + ~2000 cycles per tile before; sa1 has 1-slab layer 0s).
+        uint32_t it = 0, tcnt = 0;
+        const int glog2 = a.group > 0 ? __ffs(a.group) - 1 : 0;
+        const bool l0_small = MODE == 0 && a.cin0 <= 8 && a.cfeat <= 4;
+        int m_idx[4];
+        int m_pnt[4];
+        float m_xyz[4][3], m_cen[4][3], m_f[4][4];
+        auto meta_phase1 = [&](int64_t tile) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t lg = tile * TC_ROWS + lane + 32 * k;
+                m_idx[k] = lg < a.rows ? __ldg(a.idx + lg) : 0;
+            }
+        };
+        auto meta_phase2 = [&](int64_t tile) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t lg = tile * TC_ROWS + lane + 32 * k;
+                const bool ok = lg < a.rows;
+                const uint32_t cen = (uint32_t)(lg >> glog2);                  // rows / group < 2^31 (host check)
+                const int pnt = (int)(cen / (uint32_t)a.s) * a.n + m_idx[k];   // b * n + idx < 2^31 (host check)
+                m_pnt[k] = ok ? pnt : -1;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    m_xyz[k][j] = ok ? __ldg(a.xyz + (int64_t)pnt * 3 + j) : 0.f;
+                    m_cen[k][j] = ok ? __ldg(a.new_xyz + (int64_t)cen * 3 + j) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m_f[k][j] = (ok && l0_small && j < a.cfeat) ? __ldg(a.feats + (int64_t)pnt * a.cfeat + j) : 0.f;
+            }
+        };
+        auto meta_phase3 = [&](uint32_t tc) {            // tc = this CTA's running tile count of the tile described
+            const uint32_t buf = tc & 1, use = tc >> 1;
+            mbar_wait_warp(&meta_empty[buf], (use & 1) ^ 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float4 *dst = meta_s + ((size_t)buf * TC_ROWS + lane + 32 * k) * 2;
+                dst[0] = make_float4(__int_as_float(m_pnt[k]), __fsub_rn(m_xyz[k][0], m_cen[k][0]), __fsub_rn(m_xyz[k][1], m_cen[k][1]),
+                                     __fsub_rn(m_xyz[k][2], m_cen[k][2]));
+                dst[1] = make_float4(m_f[k][0], m_f[k][1], m_f[k][2], m_f[k][3]);
+            }
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&meta_full[buf]);
+            __syncwarp();
+        };
+        if (MODE == 0 && blockIdx.x < a.ntiles) {
+            meta_phase1(blockIdx.x);
+            meta_phase2(blockIdx.x);
+            meta_phase3(0);
+        }
+        for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcnt) {
+            const int64_t tile_next = tile + gridDim.x;
+            const bool has_next = MODE == 0 && tile_next < a.ntiles;
+            int nissued = 0;
             for (int l = 0; l < a.nlayers; ++l) {
                 const int nslab = a.kpad[l] / KC;
                 const uint32_t bytes = 2u * NCHUNK * (uint32_t)NPAD(l) * 16u;
@@ -413,7 +473,18 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                         }
                     }
                     __syncwarp();
+                    if (has_next) {     // one metadata phase after each of the first three copies
+                        if (nissued == 0) meta_phase1(tile_next);
+                        else if (nissued == 1) meta_phase2(tile_next);
+                        else if (nissued == 2) meta_phase3(tcnt + 1);
+                    }
+                    ++nissued;
                 }
+            }
+            if (has_next) {             // tiles with fewer than three slabs
+                if (nissued < 1) meta_phase1(tile_next);
+                if (nissued < 2) meta_phase2(tile_next);
+                if (nissued < 3) meta_phase3(tcnt + 1);
             }
         }
     } else {
@@ -448,38 +519,12 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
         auto unit_idx = [&](int u) { return lcq + (US == 2 ? u * LPR : 0); };                     // unit within the slab
         const int glog2 = a.group > 0 ? __ffs(a.group) - 1 : 0;
 
-        struct RowMeta {                      // one tile row of the layer-0 loader
+        struct RowMeta {                      // dense mode: one tile row of the layer-0 loader (SA rows come from the metadata ring)
             bool valid;
-            const float *pa, *pb;             // SA: feature row (or null); dense: rows of the two input segments
-            float q[3];                       // SA: point coordinates (the centroid is subtracted where they are used)
+            const float *pa, *pb;             // rows of the two input segments
         };
-        // SA: a tile starts with two dependent L2 round trips (neighbour index -> coordinates / feature
-        // row).  They are taken off the critical path with L1 prefetches issued while the PREVIOUS tile
-        // runs (index line after layer 0, the rows it points to before the last epilogue); nothing is
-        // carried in registers across the tile boundary.
-        auto prefetch_l1 = [](const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); };
-        auto meta_prefetch_idx = [&](int64_t tile) {
-            if (MODE != 0 || lcq != 0) return;
-#pragma unroll
-            for (int ri = 0; ri < RS; ++ri) {
-                const int64_t lg = tile * TC_ROWS + warp * ROWS_W + ri * RPI + lrow;
-                if (lg < a.rows && (lrow & 7) == 0) prefetch_l1(a.idx + lg);      // 8 rows = one 32-byte sector
-            }
-        };
-        auto meta_prefetch_rows = [&](int64_t tile) {
-            if (MODE != 0 || lcq != 0) return;
-#pragma unroll
-            for (int ri = 0; ri < RS; ++ri) {
-                const int64_t lg = tile * TC_ROWS + warp * ROWS_W + ri * RPI + lrow;
-                if (lg >= a.rows) continue;
-                const uint32_t cen = (uint32_t)(lg >> glog2);                      // rows / group < 2^31 (host check)
-                const int64_t pnt = (int64_t)(cen / (uint32_t)a.s) * a.n + __ldg(a.idx + lg);
-                prefetch_l1(a.xyz + pnt * 3);
-                prefetch_l1(a.xyz + pnt * 3 + 2);
-                if (a.feats) prefetch_l1(a.feats + pnt * a.cfeat);
-                if (lrow == 0) prefetch_l1(a.new_xyz + (int64_t)cen * 3 + 2);
-            }
-        };
+        const bool l0_small = MODE == 0 && a.cin0 <= 8 && a.cfeat <= 4;   // SA layer 0 entirely inside the metadata ring
+        uint32_t tcnt = 0;                    // this CTA's running tile count (metadata ring slot and parity)
 
         auto warp_wait = [&](uint64_t *bar, uint32_t parity) {   // one lane polls, the warp follows
             if (lane == 0) mbar_wait(bar, parity);
@@ -554,37 +599,22 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
         for (int64_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             const int64_t grow = tile * TC_ROWS + r;     // this thread's row in layers > 0 and the epilogue
             const bool valid = grow < a.rows;
-            const int64_t tile_next = tile + gridDim.x;
             TC_STAMP(0);
             // ---- layer-0 row metadata
             RowMeta meta[RS];
-            float cq[3] = {0.f, 0.f, 0.f};   // SA: the centroid of this warp's rows (ROWS_W <= 32 <= group: one centroid per warp and tile)
-            if (MODE == 0) {
-                const int64_t lg0 = tile * TC_ROWS + warp * ROWS_W;
-                if (lg0 < a.rows) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) cq[j] = __ldg(a.new_xyz + (lg0 >> glog2) * 3 + j);
-                }
-            }
 #pragma unroll
             for (int ri = 0; ri < RS; ++ri) {
                 const int64_t lg = tile * TC_ROWS + warp * ROWS_W + ri * RPI + lrow;
-                meta[ri].valid = lg < a.rows;
+                meta[ri].valid = MODE == 1 && lg < a.rows;
                 meta[ri].pa = meta[ri].pb = nullptr;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) meta[ri].q[j] = 0.f;
-                if (!meta[ri].valid) continue;
-                if (MODE == 0) {
-                    const uint32_t cen = (uint32_t)(lg >> glog2);
-                    const int64_t pnt = (int64_t)(cen / (uint32_t)a.s) * a.n + __ldg(a.idx + lg);
-                    meta[ri].pa = a.feats ? a.feats + pnt * a.cfeat : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) meta[ri].q[j] = __ldg(a.xyz + pnt * 3 + j);
-                } else {
+                if (meta[ri].valid) {
                     meta[ri].pa = a.segA ? a.segA + lg * a.ldA : nullptr;
                     meta[ri].pb = a.segB ? a.segB + (a.bcast ? lg / a.bcast : lg) * a.ldB : nullptr;
                 }
             }
+            // SA: this tile's slot of the metadata ring (filled by the TMA warp during the previous tile)
+            const float4 *mrow = meta_s + ((size_t)(tcnt & 1) * TC_ROWS + warp * ROWS_W + lrow) * 2;
+            if (MODE == 0) warp_wait(&meta_full[tcnt & 1], (tcnt >> 1) & 1);
             if (MODE == 1 && a.in_scale) {
                 // a tile lies inside one cloud (rows_per_cloud % 128 == 0, checked on the host): stage the
                 // cloud's scale/shift rows (GroupNorm + ReLU of the producer layer) in shared memory
@@ -599,16 +629,38 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                     aff_cloud = cloud;
                 }
             }
-            // 8 consecutive layer-0 channels from c0 of one row
-            auto load_unit = [&](const RowMeta &m, int c0, float (&x)[8]) {
+            // 8 consecutive layer-0 channels from c0 of one row (row set ri of this lane)
+            auto load_unit = [&](int ri, int c0, float (&x)[8]) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = 0.f;
-                if (!m.valid || c0 >= a.cin0 || (a.dbg & 65)) return;   // padding rows / channels (probes: no gather)
+                if (c0 >= a.cin0 || (a.dbg & 65)) return;             // padding channels (probes: no gather)
+                const float *pa = nullptr, *pb = nullptr;
+                float dx = 0.f, dy = 0.f, dz = 0.f;
+                if (MODE == 0) {
+                    const float4 m0 = mrow[ri * RPI * 2];
+                    const int pnt = __float_as_int(m0.x);
+                    if (pnt < 0) return;                                  // row past the end
+                    dx = m0.y; dy = m0.z; dz = m0.w;
+                    if (l0_small) {                                       // [f0 .. f(cfeat-1), dx, dy, dz]: no global access at all
+                        const float4 m1 = mrow[ri * RPI * 2 + 1];
+                        const float f[4] = {m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int t = j - a.cfeat;
+                            x[j] = t < 0 ? (j < 4 ? f[j < 4 ? j : 0] : 0.f) : (t == 0 ? dx : (t == 1 ? dy : (t == 2 ? dz : 0.f)));
+                        }
+                        return;
+                    }
+                    pa = a.feats ? a.feats + (int64_t)pnt * a.cfeat : nullptr;
+                } else {
+                    if (!meta[ri].valid) return;                          // row past the end
+                    pa = meta[ri].pa; pb = meta[ri].pb;
+                }
                 const int ca = MODE == 0 ? a.cfeat : a.ca;            // width of the leading segment
                 const int na = ca - c0;                               // its channels left from c0
                 const float *vp = nullptr;                            // 8 contiguous floats?
-                if (na >= 8) vp = m.pa + c0;
-                else if (MODE == 1 && na <= 0 && a.cb + na >= 8) vp = m.pb - na;
+                if (na >= 8) vp = pa + c0;
+                else if (MODE == 1 && na <= 0 && a.cb + na >= 8) vp = pb - na;
                 const uintptr_t al = reinterpret_cast<uintptr_t>(vp);
                 if (vp && (al & 31) == 0) {
                     asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -624,9 +676,9 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int t = j - na;                         // channel index within the trailing segment
-                        if (t < 0) x[j] = __ldg(m.pa + c0 + j);
-                        else if (MODE == 0) x[j] = t == 0 ? __fsub_rn(m.q[0], cq[0]) : (t == 1 ? __fsub_rn(m.q[1], cq[1]) : (t == 2 ? __fsub_rn(m.q[2], cq[2]) : 0.f));
-                        else if (t < a.cb) x[j] = __ldg(m.pb + t);
+                        if (t < 0) x[j] = __ldg(pa + c0 + j);
+                        else if (MODE == 0) x[j] = t == 0 ? dx : (t == 1 ? dy : (t == 2 ? dz : 0.f));
+                        else if (t < a.cb) x[j] = __ldg(pb + t);
                     }
                 }
             };
@@ -657,7 +709,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 float b0[2][8], b1[PF == 2 ? 2 : 1][8];
                 auto load_slab = [&](int s, float (&buf)[2][8]) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) load_unit(meta[RS == 2 ? u : 0], s * KC + 8 * unit_idx(u), buf[u]);
+                    for (int u = 0; u < 2; ++u) load_unit(RS == 2 ? u : 0, s * KC + 8 * unit_idx(u), buf[u]);
                 };
                 auto step = [&](int s, float (&buf)[2][8]) {   // buf holds slab s and is refilled with slab s + PF
                     acquire(it);
@@ -688,7 +740,11 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                     for (int s = 0; s < nslab; ++s) step(s, b0);
                 }
             }
-            if (tile_next < a.ntiles) meta_prefetch_idx(tile_next);
+            if (MODE == 0) {              // layer 0 has read this tile's metadata: the slot may be refilled
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&meta_empty[tcnt & 1]);
+            }
+            ++tcnt;
             TC_STAMP(2);
             // ---------------- layers 1..L-1: previous accumulator -> next operand ----------------
             int bias_off = 0;
@@ -732,7 +788,6 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 bias_off += NPAD(l - 1) + TC_BIAS_PAD;
                 TC_STAMP(20 + l);
             }
-            if (tile_next < a.ntiles) meta_prefetch_rows(tile_next);
             // ---------------- last epilogue ----------------
             {
                 const int l = a.nlayers - 1;
@@ -784,7 +839,22 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                     }
                     asm volatile("bar.sync 1, %0;" ::"n"(PROD) : "memory");   // red is reused by the next tile
                 } else {
-                    // row-major accumulator: the groups alternate 16-column chunks of the thread's row
+                    // row-major accumulator: the groups alternate 16-column chunks of the thread's row.  A thread
+                    // owns a ROW of the accumulator, so storing it directly makes every store instruction touch 32
+                    // rows (32 cache lines, half a sector each).  The warp's 32 x 16 block is instead transposed
+                    // through shared memory so that a store instruction writes 8 rows x 64 contiguous bytes.
+                    // Staging lives in the A-operand stages, which are idle here (every MMA of the tile has
+                    // completed): each warp uses only the bytes IT writes in layer 0 (rows warp*ROWS_W.. of every
+                    // chunk), so a warp that runs ahead into the next tile's layer 0 cannot clobber it, and nobody
+                    // reaches layer 1 of the next tile before all warps have left this epilogue.
+                    constexpr int SEG = ROWS_W * 16;                  // contiguous bytes this warp owns per operand chunk
+                    static_assert(2048 / SEG <= NCHUNK * 2 * (int)NST, "staging does not fit the warp's share of the A stages");
+                    auto stg = [&](int o) -> uint8_t * {               // byte o of the warp's 2 KB staging tile
+                        const int seg = o / SEG;
+                        return a_stage + (size_t)(seg % NCHUNK) * TC_CHUNK_BYTES + (size_t)(seg / NCHUNK) * A_PLANE + warp * SEG + (o % SEG);
+                    };
+                    const int64_t row0 = tile * TC_ROWS + (warp & 3) * 32;        // first row of this warp's TMEM lane quarter
+                    const bool vec_ok = ((reinterpret_cast<uintptr_t>(a.out + col_off) & 15) == 0) && ((a.ldo & 3) == 0);
                     const uint32_t tsrc = tbase;
                     uint32_t v[16];
                     int c0 = cg;
@@ -797,21 +867,34 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
 #pragma unroll
                         for (int j = 0; j < 16; ++j) asm volatile("" : "+f"(x[j]));
                         if (c0 + KC < npad) tmem_ld_32x16(tsrc + (uint32_t)(c0 + KC), v);
-                        if (!valid) continue;
                         if (a.relu_last) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
                         }
-                        float *dst = a.out + grow * a.ldo + col_off + c0;
-                        if (c0 + 16 <= cout_last && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                        // row `lane`, 16-byte quad q -> slot (q ^ (lane >> 1)) & 3 of the row's 64 bytes: conflict-free both ways
 #pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                *reinterpret_cast<float4 *>(dst + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-                        } else {
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4 *>(stg(lane * 64 + ((q ^ (lane >> 1)) & 3) * 16)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                        __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < cout_last) dst[j] = x[j];
+                        for (int i = 0; i < 4; ++i) {
+                            const int R = (lane >> 2) + 8 * i, q = lane & 3;
+                            const float4 t = *reinterpret_cast<const float4 *>(stg(R * 64 + ((q ^ (R >> 1)) & 3) * 16));
+                            const int64_t orow = row0 + R;
+                            const int c = c0 + 4 * q;
+                            if (orow < a.rows && c < cout_last) {
+                                float *dst = a.out + orow * a.ldo + col_off + c;
+                                if (vec_ok && c + 4 <= cout_last) {
+                                    *reinterpret_cast<float4 *>(dst) = t;
+                                } else {
+                                    dst[0] = t.x;
+                                    if (c + 1 < cout_last) dst[1] = t.y;
+                                    if (c + 2 < cout_last) dst[2] = t.z;
+                                    if (c + 3 < cout_last) dst[3] = t.w;
+                                }
+                            }
                         }
+                        __syncwarp();                                 // the next chunk reuses the staging tile
                     }
                 }
                 tcgen05_fence_before();
@@ -942,7 +1025,7 @@ static TcLayout tc_layout_v(const captra_mlp_desc &d, bool f16, bool small) {
     L.tmem_cols = d.nlayers > 1 ? 2 * L.region_cols : L.region_cols;
     L.target_occ = 1;
     // LARGE: 4 pipeline stages if they fit in 227 KB, else 2.  SMALL: 2 stages, two CTAs per SM.
-    const size_t fixed = (size_t)L.bias_floats * 4 + 256 + 4096;   // biases, slack, the grouped epilogue's [4][256] buffer
+    const size_t fixed = (size_t)L.bias_floats * 4 + 256 + 4096 + 8192;   // biases, slack, the grouped epilogue's [4][256] buffer, the SA metadata ring
     const size_t per_stage = (size_t)TC_A_STAGE + L.wstage_bytes;
     const size_t budget = small ? (size_t)(227 * 1024) / 2 - 2048 : (size_t)225 * 1024;
     L.nstages = (!small && fixed + 4 * per_stage <= budget) ? 4 : 2;
@@ -1042,7 +1125,8 @@ int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const
                   float *out, int64_t ldo, int col_off, bool f16, cudaStream_t stream) {
     CAPTRA_REQUIRE(k == 32 || k == 64 || k == 128, "sa_mlp_max(tc): nsample must be 32, 64 or 128 (got %d)", k);
     CAPTRA_REQUIRE(d->relu_last, "sa_mlp_max(tc): the max epilogue needs a ReLU after the last layer");
-    CAPTRA_REQUIRE((int64_t)b * s < 2147483647LL, "sa_mlp_max(tc): too many centroids (b * s = %lld)", (long long)b * s);
+    CAPTRA_REQUIRE((int64_t)b * s < 2147483647LL && (int64_t)b * n < 2147483647LL,
+                   "sa_mlp_max(tc): too many centroids or points (b * s = %lld, b * n = %lld)", (long long)b * s, (long long)b * n);
     TcArgs a{};
     size_t smem;
     int rc = tc_fill(a, d, packed, f16, &smem);
@@ -1091,46 +1175,65 @@ int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const flo
 // `cpg` adjacent channels over all npts points of one cloud (blocks.py:73 GroupNorm(C/2, C)).
 //   scale[b,c] = gamma[c] * rstd(b,g),  shift[b,c] = beta[c] - mean(b,g) * scale[b,c]
 // so the consumer layer applies GroupNorm + ReLU as relu(y*scale + shift) while loading its input.
-// One CTA per (cloud, 64-channel block): coalesced 256-byte row segments, fp32 partials per thread,
-// fp64 combine.
+// One CTA per (cloud, 32-channel block): a warp reads 4 rows x 128 contiguous bytes per instruction, 8 loads in
+// flight per thread (the op is a pure HBM stream: B*npts*C*4 bytes in, 2*B*C*4 out), fp32 partials per thread,
+// fp64 combine.  512 CTAs for the RotationRegressor shapes, all resident at once.
 // ------------------------------------------------------------------------------------------------
+constexpr int GN_CB = 32;       // channels per CTA
+constexpr int GN_TY = 32;       // rows in flight per pass (256 threads = 8 x 32)
+constexpr int GN_UNROLL = 8;
 __global__ void __launch_bounds__(256) group_norm_affine_kernel(int npts, int C, int cpg, const float *__restrict__ y, int64_t ld,
                                                                 const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                 float eps, float *__restrict__ scale, float *__restrict__ shift) {
-    __shared__ double s_sum[16][64], s_sq[16][64];
-    const int b = blockIdx.y, cb = blockIdx.x * 64;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    __shared__ double s_sum[GN_TY][GN_CB], s_sq[GN_TY][GN_CB];
+    const int b = blockIdx.y, cb = blockIdx.x * GN_CB;
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
     const int c0 = cb + tx * 4;
     float sm[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0};
     if (c0 < C) {
         const float *base = y + ((size_t)b * npts) * ld + c0;
         const bool vec = (c0 + 4 <= C) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((ld & 3) == 0);
-        for (int r = ty; r < npts; r += 16) {
-            float v[4];
-            if (vec) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(base + (size_t)r * ld));
-                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-            } else {
+        if (vec) {
+            int r = ty;
+            for (; r + (GN_UNROLL - 1) * GN_TY < npts; r += GN_UNROLL * GN_TY) {
+                float4 t[GN_UNROLL];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = (c0 + j < C) ? __ldg(base + (size_t)r * ld + j) : 0.f;
+                for (int u = 0; u < GN_UNROLL; ++u) t[u] = __ldg(reinterpret_cast<const float4 *>(base + (size_t)(r + u * GN_TY) * ld));
+#pragma unroll
+                for (int u = 0; u < GN_UNROLL; ++u) {
+                    sm[0] += t[u].x; sm[1] += t[u].y; sm[2] += t[u].z; sm[3] += t[u].w;
+                    sq[0] = fmaf(t[u].x, t[u].x, sq[0]); sq[1] = fmaf(t[u].y, t[u].y, sq[1]);
+                    sq[2] = fmaf(t[u].z, t[u].z, sq[2]); sq[3] = fmaf(t[u].w, t[u].w, sq[3]);
+                }
             }
+            for (; r < npts; r += GN_TY) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(base + (size_t)r * ld));
+                sm[0] += t.x; sm[1] += t.y; sm[2] += t.z; sm[3] += t.w;
+                sq[0] = fmaf(t.x, t.x, sq[0]); sq[1] = fmaf(t.y, t.y, sq[1]); sq[2] = fmaf(t.z, t.z, sq[2]); sq[3] = fmaf(t.w, t.w, sq[3]);
+            }
+        } else {
+            for (int r = ty; r < npts; r += GN_TY) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { sm[j] += v[j]; sq[j] = fmaf(v[j], v[j], sq[j]); }
+                for (int j = 0; j < 4; ++j) {
+                    const float v = (c0 + j < C) ? __ldg(base + (size_t)r * ld + j) : 0.f;
+                    sm[j] += v; sq[j] = fmaf(v, v, sq[j]);
+                }
+            }
         }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { s_sum[ty][tx * 4 + j] = sm[j]; s_sq[ty][tx * 4 + j] = sq[j]; }
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < GN_CB) {
         double a = 0, q = 0;
-        for (int i = 0; i < 16; ++i) { a += s_sum[i][threadIdx.x]; q += s_sq[i][threadIdx.x]; }
+        for (int i = 0; i < GN_TY; ++i) { a += s_sum[i][threadIdx.x]; q += s_sq[i][threadIdx.x]; }
         s_sum[0][threadIdx.x] = a; s_sq[0][threadIdx.x] = q;
     }
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < GN_CB) {
         const int c = cb + threadIdx.x;
         if (c < C) {
-            const int g0 = (threadIdx.x / cpg) * cpg;   // 64 % cpg == 0 is checked on the host
+            const int g0 = (threadIdx.x / cpg) * cpg;   // GN_CB % cpg == 0 is checked on the host
             double a = 0, q = 0;
             for (int j = 0; j < cpg; ++j) { a += s_sum[0][g0 + j]; q += s_sq[0][g0 + j]; }
             const double n = (double)npts * cpg;
@@ -1152,12 +1255,12 @@ extern "C" int captra_group_norm_affine(int clouds, int npts, int c, int channel
                                         int64_t ldy, const float *gamma, const float *beta, float eps,
                                         float *scale, float *shift, captra_stream_t stream) {
     CAPTRA_REQUIRE(clouds >= 0 && npts >= 1 && c >= 1, "group_norm_affine: bad sizes");
-    CAPTRA_REQUIRE(channels_per_group >= 1 && 64 % channels_per_group == 0 && c % channels_per_group == 0,
-                   "group_norm_affine: channels_per_group must divide 64 and C");
+    CAPTRA_REQUIRE(channels_per_group >= 1 && GN_CB % channels_per_group == 0 && c % channels_per_group == 0,
+                   "group_norm_affine: channels_per_group must divide %d and C", GN_CB);
     if (clouds == 0) return CAPTRA_OK;
     CAPTRA_REQUIRE(y && scale && shift, "group_norm_affine: null pointer");
     CAPTRA_REQUIRE(clouds <= 65535, "group_norm_affine: too many clouds");
-    group_norm_affine_kernel<<<dim3(ceil_div(c, 64), clouds), 256, 0, as_stream(stream)>>>(npts, c, channels_per_group, y, ldy, gamma,
+    group_norm_affine_kernel<<<dim3(ceil_div(c, GN_CB), clouds), 256, 0, as_stream(stream)>>>(npts, c, channels_per_group, y, ldy, gamma,
                                                                                           beta, eps, scale, shift);
     CAPTRA_CHECK_LAUNCH("group_norm_affine");
     return CAPTRA_OK;

@@ -89,7 +89,30 @@ for couts in ([512], [128, 128, 128]):
     fl = 2.0 * R * sum(a * b for a, b in zip([128] + couts[:-1], couts))
     print("%-30s %8.1f us  %6.1f TFLOP/s" % ("rows 128->%s" % "-".join(map(str, couts)), us, fl / us * 1e-6))
 
+def stamps(name, fn):
+    import ctypes
+    from captra_b200 import _lib
+    L = _lib.load()
+    buf = (ctypes.c_longlong * 512)()
+    L.captra_debug_tc_timestamps(buf, 255)
+    os.environ["CAPTRA_TC_DBG"] = "32"
+    fn()
+    os.environ["CAPTRA_TC_DBG"] = "0"
+    n = L.captra_debug_tc_timestamps(buf, 255)
+    ts = [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
+    print(name, "stamps", n)
+    print("  " + "  ".join("%d->%d:%d" % (ts[i - 1][1], ts[i][1], ts[i][0] - ts[i - 1][0]) for i in range(1, min(n, 25))))
+
+
 if os.environ.get("PROBE_STAMPS"):
+    m = PackedMLP([(torch.randn(512, 512, generator=gen) / 512 ** 0.5).to(dev)], [torch.zeros(512).to(dev)], relu_last=False,
+                  impl=int(os.environ.get('PROBE_IMPL', '2')))
+    y = torch.empty(R, 512, device=dev)
+    stamps("head 512->512 affine", lambda: m.rows_affine(x512, sc, sh, 4096, out=y))
+    m = mk(128, [512])
+    stamps("rows 128->512", lambda: m.rows(x128))
+    m = mk(128, [128, 128, 128])
+    stamps("rows 128->128-128-128", lambda: m.rows(x128))
     import ctypes
     from captra_b200 import _lib
     L = _lib.load()
