@@ -159,7 +159,7 @@ struct TcArgs {
     int f16, small;
     int cin0;                                   // true layer-0 width
     int tpose;                                  // grouped max: the last layer is computed transposed (channels in TMEM lanes)
-    int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A production, 2 no W copies, 4 no MMAs, 64 no layer-0 gather, 32 phase stamps
+    int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A production, 2 no W copies, 4 no MMAs, 8 no proxy fence, 64 no layer-0 gather, 128 no TMEM reads in the producers, 32 phase stamps
 };
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t *smem_result, uint32_t ncols) {
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
         auto release = [&](uint32_t i) {      // hand the filled stage to the MMA thread
             // every writer fences its own generic-proxy stores towards the async proxy; one elected
             // lane per warp then arrives
-            fence_proxy_async_smem();
+            if (!(a.dbg & 8)) fence_proxy_async_smem();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[i & (NST - 1)]);
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 tcgen05_fence_after();
                 TC_STAMP(10 + l);
                 uint32_t v[16];
-                if (cg < kreal && !(a.dbg & 1)) tmem_ld_32x16(tsrc, v);
+                if (cg < kreal && !(a.dbg & 129)) tmem_ld_32x16(tsrc, v);
                 for (int s = 0; s < nslab; ++s, ++it) {
                     const int c0 = s * KC + cg;
                     const bool active = c0 < kreal && !(a.dbg & 1);
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                         // before it, so the compiler does not copy v to keep the old values alive)
 #pragma unroll
                         for (int j = 0; j < 16; ++j) asm volatile("" : "+f"(x[j]));
-                        if (s + 1 < nslab && c0 + KC < kreal) tmem_ld_32x16(tsrc + (uint32_t)((s + 1) * KC), v);
+                        if (s + 1 < nslab && c0 + KC < kreal && !(a.dbg & 128)) tmem_ld_32x16(tsrc + (uint32_t)((s + 1) * KC), v);
                         convert(x, std::true_type{}, p);
                     }
                     acquire(it);
