@@ -221,7 +221,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=4, help="clouds per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="clouds per CPU-baseline step (about 10 s of host work for 1 + 5 steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--dump-kernels", default=None, help="write the full per-launch table of the profiled pass (JSON) to this path")
@@ -413,7 +413,7 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_arm(args.workload, 2, 1, args.cpu_sample)
+        r = cpu_reference_arm(args.workload, 5, 1, args.cpu_sample)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
