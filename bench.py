@@ -128,6 +128,19 @@ def algorithmic(tag):
         wbytes = 4 * sum(a * b for a, b in zip([cin] + widths[:-1], widths))
         # compulsory traffic of the fused query-group-MLP-max: xyz + features once, idx, output, weights
         return 12 * B * (N + S) + 4 * B * (cin - 3) * N + 4 * B * S * K + 4 * B * S * widths[-1] + wbytes, 2 * rows * macs
+    if name == "sa_mlp_max_pre":
+        # layer 0 projected per point: this launch gathers cpre-wide projected rows and runs layers 1.. (the
+        # projection itself is a point_mlp launch of its own); only the MACs executed here are counted
+        N, S, K = int(kv["N"]), int(kv["S"]), int(kv["K"])
+        cin, widths = kv["C"].split("->")
+        cin, widths = int(cin), [int(w) for w in widths.split("-")]
+        rows = B * S * K
+        macs, last = 3 * cin, cin
+        for w in widths:
+            macs += last * w
+            last = w
+        wbytes = 4 * sum(a * b for a, b in zip([cin] + widths[:-1], widths))
+        return 12 * B * (N + S) + 4 * B * cin * N + 4 * B * S * K + 4 * B * S * widths[-1] + wbytes, 2 * rows * macs
     if name == "point_mlp":
         R, g = int(kv["R"]), int(kv["g"])
         cin, widths = kv["C"].split("->")
@@ -387,7 +400,7 @@ def main():
                 json.dump({"ms_per_step": step_avg_ms, "captra_ms_per_step": sum(k["ms_per_step"] for k in kernels), "kernels": kernels}, f, indent=1)
         top = kernels[0]
         tname = _parse(top["tag"])[0]
-        if tname in ("sa_mlp_max", "point_mlp"):
+        if tname in ("sa_mlp_max", "sa_mlp_max_pre", "point_mlp"):
             roofline = {"kernel": top["tag"], "bound": "tensor", "achieved": top["tflops"], "peak": pk["tf_sus"], "unit": "TFLOP/s",
                         "frac": top["tflops"] / pk["tf_sus"], "traffic": ncu_traffic(top["tag"]),
                         "frac_of_split_ceiling": 3.0 * top["tflops"] / pk["tf_sus"] if mlp.DEFAULT_IMPL else None,
@@ -398,7 +411,7 @@ def main():
             roofline = {"kernel": top["tag"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"], "unit": "GB/s",
                         "frac": top["hbm_frac"], "traffic": ncu_traffic(top["tag"]), "peak_source": pk["src"] + " hbm_gbs",
                         "avg_us": top["avg_us"], "share_of_step": top["share_of_step"]}
-        bq = [k for k in kernels if _parse(k["tag"])[0] in ("ball_query_multi", "sa_mlp_max")]
+        bq = [k for k in kernels if _parse(k["tag"])[0] in ("ball_query_multi", "sa_mlp_max", "sa_mlp_max_pre")]
         qg_bytes = sum(k["alg_bytes"] * k["launches_per_step"] for k in bq)
         qg_ms = sum(k["ms_per_step"] for k in bq)
         query_group = {"what": "ball_query + fused group/MLP/max launches of one step", "alg_bytes_per_step": qg_bytes,

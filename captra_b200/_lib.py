@@ -34,6 +34,7 @@ SIGNATURES = {
     "captra_three_nn_interpolate": [c_int] * 4 + [_P] * 7 + [c_int, c_i64, c_int, _P],
     "captra_mlp_pack": [_P, c_int, _P, _P],
     "captra_sa_mlp_max": [c_int] * 5 + [_P] * 7 + [c_i64, c_int, c_int, _P],
+    "captra_sa_mlp_max_pre": [c_int] * 5 + [_P, _P, _P, c_i64, _P, _P, _P, _P, _P, c_i64, c_int, c_int, _P],
     "captra_point_mlp": [c_i64, _P, c_i64, c_int, _P, c_i64, c_int, c_int, _P, _P, _P, c_i64, c_int, c_int, c_int, _P],
     "captra_group_norm_affine": [c_int] * 4 + [_P, c_i64, _P, _P, c_float, _P, _P, _P],
     "captra_point_mlp_affine": [c_i64, _P, c_i64, c_int, _P, _P, c_int, _P, _P, _P, c_i64, c_int, c_int, _P],

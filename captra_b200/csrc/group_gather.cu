@@ -122,10 +122,23 @@ static int launch_gather(const char *name, int b, int c, int n, int64_t L, const
         const int nblk = ceil_div(c, cb);
         cb = ceil_div(c, nblk);                // even out the channel blocks
         const size_t smem = (size_t)cb * n * 4;
-        // split L only while there are fewer CTAs than two per SM, keeping chunks >= 2 rows' worth of slots
+        // Split L into chunks (each >= 2 rows' worth of slots, so the staging copy stays a small part of a CTA's
+        // work) such that the CTA count fills whole waves: slots = SMs x resident CTAs per SM for this smem
+        // footprint.  (cfg5 level 1 -- 64 clouds, 196 KB per CTA -- ran 320 CTAs in 3 waves at 72 % fill.)
         int splits = 1;
         const int64_t ctas = (int64_t)b * nblk;
-        if (ctas < 2 * 148) splits = (int)std::min<int64_t>(ceil_div<int64_t>(2 * 148, ctas), std::max<int64_t>(1, L / (2 * (int64_t)n)));
+        const int occ = (int)std::max<size_t>(1, std::min<size_t>((size_t)(227u << 10) / (smem + 1024), 2048 / GS_THREADS));
+        const int64_t slots = (int64_t)sm_count() * occ;
+        const int64_t max_splits = std::max<int64_t>(1, std::min<int64_t>(L / (2 * (int64_t)n), 64));
+        if (ctas < 4 * slots) {
+            double best = -1.0;
+            for (int64_t sp = 1; sp <= max_splits; ++sp) {
+                const int64_t t = ctas * sp, waves = ceil_div<int64_t>(t, slots);
+                if (waves > 4 && sp > 1) break;
+                const double fill = (double)t / (double)(waves * slots);
+                if (fill > best + 1e-9) { best = fill; splits = (int)sp; }
+            }
+        }
         int64_t chunk = ceil_div<int64_t>(ceil_div<int64_t>(L, splits), 4) * 4;
         splits = (int)ceil_div<int64_t>(L, chunk);
         if (nblk <= 65535) {

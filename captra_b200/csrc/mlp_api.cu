@@ -15,6 +15,9 @@ int tc_pack(const captra_mlp_desc *d, void *packed, bool f16, cudaStream_t strea
 int tc_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz, const float *new_xyz,
                   const float *feats, const int *idx, const captra_mlp_desc *d, const void *packed,
                   float *out, int64_t ldo, int col_off, bool f16, cudaStream_t stream);
+int tc_sa_mlp_max_pre(int b, int n, int s, int k, int cpre, const float *xyz, const float *new_xyz, const float *pre,
+                      int64_t ldpre, const float *tab, const int *idx, const captra_mlp_desc *d, const void *packed,
+                      float *out, int64_t ldo, int col_off, bool f16, cudaStream_t stream);
 int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
                  int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
                  int group, bool f16, cudaStream_t stream);
@@ -65,6 +68,21 @@ extern "C" int captra_sa_mlp_max(int b, int n, int s, int k, int cfeat, const fl
         return tc_sa_mlp_max(b, n, s, k, cfeat, xyz, new_xyz, feats, idx, d, packed, out, ldo, col_off, impl == 2, as_stream(stream));
     set_error("sa_mlp_max: impl %d not available", impl);
     return CAPTRA_ERR_UNSUPPORTED;
+}
+
+extern "C" int captra_sa_mlp_max_pre(int b, int n, int s, int k, int cpre, const float *xyz, const float *new_xyz,
+                                     const float *pre, int64_t ldpre, const float *wxyz_bias, const int *idx,
+                                     const captra_mlp_desc *d, const void *packed, float *out, int64_t ldo,
+                                     int col_off, int impl, captra_stream_t stream) {
+    int rc = check_desc(d, "sa_mlp_max_pre");
+    if (rc) return rc;
+    CAPTRA_REQUIRE(b >= 0 && n >= 1 && s >= 0 && k >= 1 && cpre >= 1 && ldpre >= cpre, "sa_mlp_max_pre: bad sizes");
+    CAPTRA_REQUIRE(d->cin == cpre, "sa_mlp_max_pre: tail mlp cin=%d but the projected rows have %d channels", d->cin, cpre);
+    CAPTRA_REQUIRE(impl == 1 || impl == 2, "sa_mlp_max_pre: only the tcgen05 paths (impl 1, 2) implement the projected layer 0");
+    if (b == 0 || s == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(xyz && new_xyz && idx && packed && out && pre && wxyz_bias, "sa_mlp_max_pre: null pointer");
+    return tc_sa_mlp_max_pre(b, n, s, k, cpre, xyz, new_xyz, pre, ldpre, wxyz_bias, idx, d, packed, out, ldo, col_off, impl == 2,
+                             as_stream(stream));
 }
 
 extern "C" int captra_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB,

@@ -136,6 +136,26 @@ class PackedMLP:
                   out.shape[-1], col_off, impl, _lib.stream_ptr(xyz.device), device=xyz.device)
         return out
 
+    def sa_max_pre(self, xyz, new_xyz, pre, tab, idx, out, col_off=0):
+        """Fused SA scale whose layer 0 was projected per point (captra_sa_mlp_max_pre): `self` holds layers
+        1.. of the scale; pre [B*N, cpre] is a column block (row stride pre.stride(0)) of W_f * features,
+        tab [4, cpre] = the coordinate columns of the folded first-layer weight and its bias."""
+        B, N, _ = xyz.shape
+        S, K = idx.shape[1], idx.shape[2]
+        cpre = pre.shape[1]
+        f32, i32 = torch.float32, torch.int32
+        impl = self._pick(self.impl, group=K, sa=True)
+        if impl not in (1, 2) or self._layers is not None:
+            raise _lib.CaptraError("sa_max_pre: the projected layer 0 needs the fused tcgen05 path")
+        if not (pre.is_cuda and pre.dtype == f32 and pre.dim() == 2 and pre.stride(1) == 1 and pre.shape[0] == B * N):
+            raise _lib.CaptraError("sa_max_pre: pre must be a CUDA fp32 [B*N, cpre] block with contiguous channels")
+        _lib.call("sa_mlp_max_pre[B=%d,N=%d,S=%d,K=%d,C=%d->%s,impl=%d]" % (B, N, S, K, cpre, "-".join(map(str, self.couts)), impl),
+                  _lib.load().captra_sa_mlp_max_pre, B, N, S, K, cpre, _lib.ptr(xyz, f32, "xyz"), _lib.ptr(new_xyz, f32, "new_xyz"),
+                  pre.data_ptr(), pre.stride(0), _lib.ptr(tab, f32, "tab"), _lib.ptr(idx, i32, "idx"),
+                  ctypes.byref(self.desc), self._pack(impl).data_ptr(), _lib.ptr(out, f32, "out"),
+                  out.shape[-1], col_off, impl, _lib.stream_ptr(xyz.device), device=xyz.device)
+        return out
+
     def rows(self, segA, segB=None, bcast_rows=0, group=0, out=None, col_off=0):
         """Pointwise MLP.  segA [R,ca] / segB [R,cb] (or [R/bcast_rows,cb]) point-major row blocks
         (last dim contiguous, arbitrary row stride); returns out [R or R/group, cout]."""

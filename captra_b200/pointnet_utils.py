@@ -7,6 +7,8 @@ Eval-mode forwards run on the fused kernels (one launch per SA scale / FP stage,
 training-mode forwards (BatchNorm batch statistics, autograd) use the same composition as the
 reference on top of this package's CUDA ops -- there is no CPU path anywhere.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -140,6 +142,11 @@ class PointNetSetAbstractionMsg(nn.Module):
             self.bn_blocks.append(bns)
         self.knn = knn
         self._cache = _FusedCache()
+        self._cache_pre = _FusedCache()
+
+    # Input feature widths from which layer 0 is projected per point instead of per (centroid, sample) row
+    # (PackedMLP.sa_max_pre): worthwhile once a point's feature row is much wider than its 3 coordinates.
+    PRE_MIN_FEAT = 32
 
     def _packed(self):
         def build():
@@ -149,6 +156,32 @@ class PointNetSetAbstractionMsg(nn.Module):
                 out.append(PackedMLP([w for w, _ in wb], [b for _, b in wb], relu_last=True))
             return out
         return self._cache.get(self, build)
+
+    def _packed_pre(self):
+        """Projected form of every scale: (projector over all scales, [(tail mlp, coordinate/bias table, column
+        offset, width)]) or None when the shapes do not qualify (few input features, one-layer scales, the
+        exact-fp32 kernel selected, first layers wider than one 256-column launch together)."""
+        def build():
+            from . import mlp as _mlp
+            if _mlp.DEFAULT_IMPL not in (1, 2) or os.environ.get("CAPTRA_SA_PRE", "1") == "0":   # knob: A/B timing
+                return None
+            folded = [[fold_conv_bn(c, b) for c, b in zip(convs, bns)] for convs, bns in zip(self.conv_blocks, self.bn_blocks)]
+            D = folded[0][0][0].shape[1] - 3
+            if D < self.PRE_MIN_FEAT or any(len(wb) < 2 for wb in folded) or sum(wb[0][0].shape[0] for wb in folded) > 256:
+                return None
+            scales, off = [], 0
+            for wb in folded:
+                W0, b0 = wb[0]
+                tail = PackedMLP([w for w, _ in wb[1:]], [b for _, b in wb[1:]], relu_last=True)
+                if tail._layers is not None or not tail._tc_supported():
+                    return None
+                tab = torch.cat([W0[:, D:D + 3].t(), b0[None, :]], 0).contiguous()      # [4, c1]: wx, wy, wz, bias
+                scales.append((tail, tab, off, W0.shape[0]))
+                off += W0.shape[0]
+            Wf = torch.cat([wb[0][0][:, :D] for wb in folded], 0).contiguous()           # [sum c1, D]
+            proj = PackedMLP([Wf], [torch.zeros(Wf.shape[0], device=Wf.device)], relu_last=False)
+            return proj, scales
+        return self._cache_pre.get(self, build)
 
     def forward_pm(self, xyz_pm, feats_pm, geom=None):
         """Fused inference path on point-major tensors: xyz [B,N,3], feats [B,N,D] or None ->
@@ -167,6 +200,17 @@ class PointNetSetAbstractionMsg(nn.Module):
                 geom["new_xyz"], geom["idxs"] = new_xyz, idxs
         out = torch.empty(xyz_pm.shape[0], self.npoint, self.out_channel, dtype=torch.float32, device=xyz_pm.device)
         off = 0
+        pre = self._packed_pre() if (feats_pm is not None and all(i.shape[2] in PackedMLP.TC_GROUPS for i in idxs)) else None
+        if pre is not None:
+            # layer 0 of all scales projected once per point (one dense launch), then gathered: the feature part
+            # of the first conv depends on the point only, and a point sits in nsample * S / N balls
+            proj, scales = pre
+            B, N, D = feats_pm.shape
+            P = proj.rows(feats_pm.reshape(B * N, D))
+            for (tail, tab, poff, c1), idx in zip(scales, idxs):
+                tail.sa_max_pre(xyz_pm, new_xyz, P[:, poff:poff + c1], tab, idx, out, col_off=off)
+                off += tail.cout
+            return new_xyz, out
         for mlp, idx in zip(self._packed(), idxs):
             mlp.sa_max(xyz_pm, new_xyz, feats_pm, idx, out, col_off=off)
             off += mlp.cout

@@ -155,6 +155,20 @@ int captra_sa_mlp_max(int b, int n, int s, int k, int cfeat, const float *xyz,
                       const captra_mlp_desc *mlp, const void *packed, float *out, int64_t ldo,
                       int col_off, int impl, captra_stream_t stream);
 
+/* The same set-abstraction scale with layer 0 PROJECTED per point.  Layer 0 is linear in
+ * [features | xyz - centroid] (pointnet_utils.py:239-246: conv -> BN -> ReLU on the concatenation), and its
+ * feature part depends on the point only, while every point sits in many balls.  The caller computes
+ *   pre[b*N + j, :] = W0[:, :cfeat] * feats[b, j, :]            (one captra_point_mlp launch, no bias / ReLU)
+ * once per cloud, and this entry forms
+ *   h0 = relu(pre[idx] + wxyz_bias[0]*dx + wxyz_bias[1]*dy + wxyz_bias[2]*dz + wxyz_bias[3])
+ * on the fly (wxyz_bias is [4][cpre]: the three coordinate columns of the BN-folded W0, then its bias) and
+ * runs layers 1.. (`mlp`, cin == cpre) and the max as above.  pre has row stride ldpre, so the scales of
+ * one MSG layer read column blocks of one projected buffer.  tcgen05 paths (impl 1, 2) only. */
+int captra_sa_mlp_max_pre(int b, int n, int s, int k, int cpre, const float *xyz, const float *new_xyz,
+                          const float *pre, int64_t ldpre, const float *wxyz_bias, const int *idx,
+                          const captra_mlp_desc *mlp, const void *packed, float *out, int64_t ldo,
+                          int col_off, int impl, captra_stream_t stream);
+
 /* Pointwise MLP on rows.  Row r of the input is the concatenation
  *   [ segA[r*ldA : +ca] , segB[(bcast_rows ? r / bcast_rows : r)*ldB : +cb] ]
  * (the torch.cat of pointnet_utils.py:185,292 and the `repeat` of :281-282 without

@@ -112,6 +112,82 @@ def test_sa_mlp_max_vs_torch(impl, N, S, K, cfeat, couts, cuda, oracle):
     assert (out[..., :8] == -3).all()
 
 
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("off,ld,ca,cb", [(0, 64, 64, 0), (4, 72, 64, 0), (1, 67, 64, 0), (0, 64, 64, 64), (0, 40, 40, 24), (8, 136, 128, 6)])
+def test_layer0_loader_alignment_paths(impl, off, ld, ca, cb, cuda):
+    """The coalesced layer-0 loader of the tensor-core kernel picks per 8-channel unit between one 32-byte
+    load, two 16-byte loads and scalar loads by the address it sees: rows that are 32-byte aligned, only
+    16-byte aligned (column offset 4), unaligned (odd row stride), and units that straddle / lie in the
+    second input segment must all give the same numbers."""
+    from captra_b200.mlp import PackedMLP
+    gen = torch.Generator().manual_seed(off + ld + ca + cb)
+    rows = 3 * 128 + 37                                                    # a partial last tile
+    big = torch.randn(rows, off + ld, generator=gen).to(cuda)
+    A = big[:, off:off + ca]
+    Bm = torch.randn(rows, cb, generator=gen).to(cuda) if cb else None
+    x = torch.cat([A, Bm], 1) if cb else A
+    for couts in ([64, 64], [256]):
+        ws, bs = _rand_mlp(ca + cb, couts, gen, cuda)
+        got = PackedMLP(ws, bs, impl=impl).rows(A, Bm)
+        torch.testing.assert_close(got, _torch_mlp(x.contiguous(), ws, bs), **TOL)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("S,K,cfeat", [(50, 32, 3), (50, 32, 0), (25, 64, 16), (13, 32, 323)])
+def test_sa_metadata_ring_partial_tiles(impl, S, K, cfeat, cuda, oracle):
+    """SA launches whose row count is not a multiple of the 128-row tile and that walk many tiles per CTA
+    slot: the TMA warp's two-tile metadata ring must stay in step with the producers, rows past the
+    end must contribute nothing, for the in-ring (<= 8 input channels) and the gathered layer 0."""
+    from captra_b200.mlp import PackedMLP
+    B, N = 1, 700
+    gen = torch.Generator().manual_seed(S * K + cfeat)
+    pts = synthetic.batch_surface_box(B, N, seed=S)[0]
+    ctr_idx = oracle.furthest_point_sample(pts, S)
+    ctr = np.stack([pts[b, ctr_idx[b]] for b in range(B)])
+    idx = oracle.ball_query(0.3, K, pts, ctr)
+    xyz, new_xyz, gidx = torch.from_numpy(pts).to(cuda), torch.from_numpy(ctr).to(cuda), torch.from_numpy(idx).to(cuda)
+    feats = torch.randn(B, N, cfeat, generator=gen).to(cuda) if cfeat else None
+    ws, bs = _rand_mlp(cfeat + 3, [32, 48, 64], gen, cuda)
+    out = torch.empty(B, S, 64, device=cuda)
+    PackedMLP(ws, bs, impl=impl).sa_max(xyz, new_xyz, feats, gidx, out)
+    bi = torch.arange(B, device=cuda).view(B, 1, 1)
+    g_xyz = xyz[bi, gidx.long()] - new_xyz.unsqueeze(2)
+    rows = torch.cat([feats[bi, gidx.long()], g_xyz], -1) if cfeat else g_xyz
+    want = _torch_mlp(rows.reshape(-1, cfeat + 3), ws, bs).view(B, S, K, -1).max(2)[0]
+    torch.testing.assert_close(out, want, **TOL)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("N,S,K,cfeat,couts", [(512, 128, 128, 320, [128, 196, 256]), (512, 128, 64, 320, [128, 128, 256]),
+                                                (600, 37, 32, 45, [40, 24, 50]), (256, 64, 64, 64, [72, 256])])
+def test_sa_mlp_max_projected_layer0(impl, N, S, K, cfeat, couts, cuda, oracle):
+    """captra_sa_mlp_max_pre: layer 0 applied per point (W_f f) and completed in the loader
+    (+ W_x (x - c) + b, ReLU) must equal the plain formulation on the concatenated rows."""
+    from captra_b200.mlp import PackedMLP
+    B = 2
+    gen = torch.Generator().manual_seed(N + K + cfeat)
+    pts = synthetic.batch_surface_box(B, N, seed=K)[0]
+    ctr_idx = oracle.furthest_point_sample(pts, S)
+    ctr = np.stack([pts[b, ctr_idx[b]] for b in range(B)])
+    idx = oracle.ball_query(0.25, K, pts, ctr)
+    xyz, new_xyz, gidx = torch.from_numpy(pts).to(cuda), torch.from_numpy(ctr).to(cuda), torch.from_numpy(idx).to(cuda)
+    feats = torch.randn(B, N, cfeat, generator=gen).to(cuda)
+    ws, bs = _rand_mlp(cfeat + 3, couts, gen, cuda)
+    c1 = couts[0]
+    proj = PackedMLP([ws[0][:, :cfeat].contiguous()], [torch.zeros(c1, device=cuda)], relu_last=False, impl=impl)
+    P = torch.full((B * N, c1 + 24), 9.0, device=cuda)                        # a column block of a wider buffer
+    proj.rows(feats.reshape(B * N, cfeat), out=P, col_off=8)
+    tab = torch.cat([ws[0][:, cfeat:].t(), bs[0][None]], 0).contiguous()
+    out = torch.full((B, S, couts[-1] + 8), -3.0, device=cuda)
+    PackedMLP(ws[1:], bs[1:], impl=impl).sa_max_pre(xyz, new_xyz, P[:, 8:8 + c1], tab, gidx, out, col_off=8)
+    bi = torch.arange(B, device=cuda).view(B, 1, 1)
+    g_xyz = xyz[bi, gidx.long()] - new_xyz.unsqueeze(2)
+    rows = torch.cat([feats[bi, gidx.long()], g_xyz], -1)
+    want = _torch_mlp(rows.reshape(-1, cfeat + 3), ws, bs).view(B, S, K, -1).max(2)[0]
+    torch.testing.assert_close(out[..., 8:], want, **TOL)
+    assert (out[..., :8] == -3).all()
+
+
 def _golden_backbone(tag, cuda):
     from captra_b200.backbones import PointNet2Msg
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "backbone.npz"))
