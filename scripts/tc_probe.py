@@ -56,17 +56,33 @@ def timeit(fn, n=5):
     return 1e3 * e0.elapsed_time(e1) / n
 
 
+# projected layer 0 (captra_sa_mlp_max_pre): the sa2 scales as the tracker runs them
+for k, idxk, couts in ((128, i2, [196, 256]), (64, i3, [128, 256])):
+    tail = mk(128, couts)
+    P = torch.randn(B * 512, 256, generator=gen).to(dev)
+    tab = torch.randn(4, 128, generator=gen).to(dev) * 0.1
+    cases.append(("sa2pre K=%d 128->%s" % (k, "-".join(map(str, couts))), tail, c1, c2, (P[:, :128], tab), idxk))
+
 DBGS = [int(v) for v in os.environ.get("PROBE_DBG", "0").split(",")]
 if os.environ.get("PROBE_CASES"):   # e.g. PROBE_CASES=0,1 keeps only those SA cases (ncu captures)
     cases = [cases[int(i)] for i in os.environ["PROBE_CASES"].split(",")]
 N_TIMED = int(os.environ.get("PROBE_N", "5"))
+
+
+def run_case(mlp, xyz, ctr, feats, idx, out):
+    if isinstance(feats, tuple):
+        mlp.sa_max_pre(xyz, ctr, feats[0], feats[1], idx, out)
+    else:
+        mlp.sa_max(xyz, ctr, feats, idx, out)
+
+
 for name, mlp, xyz, ctr, feats, idx in cases:
     out = torch.empty(B, ctr.shape[1], mlp.cout, device=dev)
     rows = B * ctr.shape[1] * idx.shape[2]
     fl = 2.0 * rows * sum(a * b for a, b in zip([mlp.cin] + mlp.couts[:-1], mlp.couts))
     for dbg in DBGS:   # CAPTRA_TC_DBG knobs: results are garbage, only the time matters
         os.environ["CAPTRA_TC_DBG"] = str(dbg)
-        us = timeit(lambda: mlp.sa_max(xyz, ctr, feats, idx, out), N_TIMED)
+        us = timeit(lambda: run_case(mlp, xyz, ctr, feats, idx, out), N_TIMED)
         print("%-30s dbg=%2d %8.1f us  %6.1f TFLOP/s (algorithmic)" % (name, dbg, us, fl / us * 1e-6))
 os.environ["CAPTRA_TC_DBG"] = "0"
 
@@ -121,7 +137,7 @@ if os.environ.get("PROBE_STAMPS"):
         buf = (ctypes.c_longlong * 512)()
         L.captra_debug_tc_timestamps(buf, 255)
         os.environ["CAPTRA_TC_DBG"] = "32"
-        mlp.sa_max(xyz, ctr, feats, idx, out)
+        run_case(mlp, xyz, ctr, feats, idx, out)
         os.environ["CAPTRA_TC_DBG"] = "0"
         n = L.captra_debug_tc_timestamps(buf, 255)
         ts = [(buf[2 * i], buf[2 * i + 1]) for i in range(n)]
