@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
     uint8_t *w_stage = a_stage + (size_t)NST * A_STAGE;                   // NST x wstage_bytes
     float *bias_s = reinterpret_cast<float *>(w_stage + (size_t)NST * a.wstage_bytes);
     float *aff_s = bias_s + a.bias_floats;                                // [2][aff_pad] when a.aff_pad > 0
-    float4 *meta_s = reinterpret_cast<float4 *>(aff_s + 2 * a.aff_pad + 4 * a.pre_pad);   // [2 tiles][128 rows][2]: {point, dx, dy, dz}, {first 4 features}
+    float4 *meta_s = reinterpret_cast<float4 *>(aff_s + 2 * a.aff_pad + 4 * a.pre_pad);   // [2 tiles][128 rows][2]: {point, dx, dy, dz} or the assembled 8-channel row
     float *red = reinterpret_cast<float *>(meta_s + 2 * TC_ROWS * 2);     // [4][256] partial maxima of the grouped epilogue (also the slack the
                                                                           // transposed last layer's 128-row weight reads may run into)
 
@@ -445,13 +445,27 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
         };
         auto meta_phase3 = [&](uint32_t tc) {            // tc = this CTA's running tile count of the tile described
             const uint32_t buf = tc & 1, use = tc >> 1;
-            mbar_wait_warp(&meta_empty[buf], (use & 1) ^ 1);
+            mbar_wait_warp_relaxed(&meta_empty[buf], (use & 1) ^ 1);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float4 *dst = meta_s + ((size_t)buf * TC_ROWS + lane + 32 * k) * 2;
-                dst[0] = make_float4(__int_as_float(m_pnt[k]), __fsub_rn(m_xyz[k][0], m_cen[k][0]), __fsub_rn(m_xyz[k][1], m_cen[k][1]),
-                                     __fsub_rn(m_xyz[k][2], m_cen[k][2]));
-                dst[1] = make_float4(m_f[k][0], m_f[k][1], m_f[k][2], m_f[k][3]);
+                const float dx = __fsub_rn(m_xyz[k][0], m_cen[k][0]), dy = __fsub_rn(m_xyz[k][1], m_cen[k][1]),
+                            dz = __fsub_rn(m_xyz[k][2], m_cen[k][2]);
+                if (l0_small) {
+                    // the whole layer-0 row, assembled here once: [f0 .. f(cfeat-1), dx, dy, dz, 0 ..] (zeros past the end)
+                    float in[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int t = j - a.cfeat;
+                        const float v = t < 0 ? (j < 4 ? m_f[k][j < 4 ? j : 0] : 0.f) : (t == 0 ? dx : (t == 1 ? dy : (t == 2 ? dz : 0.f)));
+                        in[j] = m_pnt[k] >= 0 ? v : 0.f;
+                    }
+                    dst[0] = make_float4(in[0], in[1], in[2], in[3]);
+                    dst[1] = make_float4(in[4], in[5], in[6], in[7]);
+                } else {
+                    dst[0] = make_float4(__int_as_float(m_pnt[k]), dx, dy, dz);
+                    dst[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             __syncwarp();
             if (elect_one()) mbar_arrive(&meta_full[buf]);
@@ -472,7 +486,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(WPK(l));
                 for (int s = 0; s < nslab; ++s, ++it) {
                     const uint32_t st = it & (NST - 1), ph = (it >> nst_log2) & 1;
-                    mbar_wait_warp(&empty[st], ph ^ 1);
+                    mbar_wait_warp_relaxed(&empty[st], ph ^ 1);
                     if (elect_one()) {
                         if (a.dbg & 2) {
                             mbar_arrive(&full[st]);
@@ -647,19 +661,15 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 float dx = 0.f, dy = 0.f, dz = 0.f;
                 if (MODE == 0) {
                     const float4 m0 = mrow[ri * RPI * 2];
+                    if (l0_small) {                                       // the assembled row itself: no global access at all
+                        const float4 m1 = mrow[ri * RPI * 2 + 1];
+                        x[0] = m0.x; x[1] = m0.y; x[2] = m0.z; x[3] = m0.w;
+                        x[4] = m1.x; x[5] = m1.y; x[6] = m1.z; x[7] = m1.w;
+                        return;
+                    }
                     const int pnt = __float_as_int(m0.x);
                     if (pnt < 0) return;                                  // row past the end
                     dx = m0.y; dy = m0.z; dz = m0.w;
-                    if (l0_small) {                                       // [f0 .. f(cfeat-1), dx, dy, dz]: no global access at all
-                        const float4 m1 = mrow[ri * RPI * 2 + 1];
-                        const float f[4] = {m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int t = j - a.cfeat;
-                            x[j] = t < 0 ? (j < 4 ? f[j < 4 ? j : 0] : 0.f) : (t == 0 ? dx : (t == 1 ? dy : (t == 2 ? dz : 0.f)));
-                        }
-                        return;
-                    }
                     pa = a.feats ? a.feats + (int64_t)pnt * a.ldf : nullptr;
                 } else {
                     if (!meta[ri].valid) return;                          // row past the end

@@ -44,6 +44,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
     while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {}
 }
+// The same for a warp whose wake-up latency does not matter (the weight / metadata producer): back off between
+// polls, because the polling loops of idle warps compete with the operand producers for issue slots (ncu on the
+// sa1 launches: 27 % of all issued instructions were try_wait loops, most of them from the two idle service warps).
+__device__ __forceinline__ void mbar_wait_warp_relaxed(uint64_t *bar, uint32_t parity) {
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) __nanosleep(256);
+}
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
