@@ -38,6 +38,8 @@ SIGNATURES = {
     "captra_point_mlp": [c_i64, _P, c_i64, c_int, _P, c_i64, c_int, c_int, _P, _P, _P, c_i64, c_int, c_int, c_int, _P],
     "captra_group_norm_affine": [c_int] * 4 + [_P, c_i64, _P, _P, c_float, _P, _P, _P],
     "captra_point_mlp_affine": [c_i64, _P, c_i64, c_int, _P, _P, c_int, _P, _P, _P, c_i64, c_int, c_int, _P],
+    "captra_point_mlp_gnstats": [c_i64, _P, c_i64, c_int, _P, _P, c_int, _P, _P, _P, c_i64, c_int, _P, c_int, _P],
+    "captra_group_norm_finalize": [c_int] * 4 + [_P, _P, _P, c_float, _P, _P, _P],
     "captra_debug_tc_timestamps": [_P, c_int],
     "captra_f16_overflow_flag": [c_int],
     "captra_debug_umma_gemm": [c_int, c_int, _P, _P, _P, c_int, _P],

@@ -24,6 +24,9 @@ int tc_point_mlp(int64_t rows, const float *segA, int64_t ldA, int ca, const flo
 int tc_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale, const float *in_shift,
                         int rows_per_cloud, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
                         int col_off, bool f16, cudaStream_t stream);
+int tc_point_mlp_gnstats(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale, const float *in_shift,
+                         int rows_per_cloud, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
+                         int col_off, float *stats, bool f16, cudaStream_t stream);
 }  // namespace captra
 
 using namespace captra;
@@ -116,4 +119,21 @@ extern "C" int captra_point_mlp_affine(int64_t rows, const float *x, int64_t ldx
     if (rows == 0) return CAPTRA_OK;
     CAPTRA_REQUIRE(x && in_scale && in_shift && packed && y, "point_mlp_affine: null pointer");
     return tc_point_mlp_affine(rows, x, ldx, cin, in_scale, in_shift, rows_per_cloud, d, packed, y, ldy, col_off, impl == 2, as_stream(stream));
+}
+
+extern "C" int captra_point_mlp_gnstats(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale,
+                                        const float *in_shift, int rows_per_cloud, const captra_mlp_desc *d,
+                                        const void *packed, float *y, int64_t ldy, int col_off, float *stats, int impl,
+                                        captra_stream_t stream) {
+    int rc = check_desc(d, "point_mlp_gnstats");
+    if (rc) return rc;
+    CAPTRA_REQUIRE(rows >= 0 && cin >= 1 && rows_per_cloud >= 1, "point_mlp_gnstats: bad sizes");
+    CAPTRA_REQUIRE(d->cin == cin, "point_mlp_gnstats: mlp cin=%d but input has %d channels", d->cin, cin);
+    CAPTRA_REQUIRE(impl == 1 || impl == 2, "point_mlp_gnstats: only the tcgen05 paths (impl 1, 2) fuse the statistics");
+    CAPTRA_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), "point_mlp_gnstats: scale and shift come together");
+    CAPTRA_REQUIRE(rows_per_cloud % 128 == 0, "point_mlp_gnstats: rows_per_cloud must be a multiple of 128 (got %d)", rows_per_cloud);
+    if (rows == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(x && packed && y && stats, "point_mlp_gnstats: null pointer");
+    return tc_point_mlp_gnstats(rows, x, ldx, cin, in_scale, in_shift, rows_per_cloud, d, packed, y, ldy, col_off, stats, impl == 2,
+                                as_stream(stream));
 }

@@ -157,6 +157,7 @@ struct TcArgs {
     const float *segA; int64_t ldA; int ca; const float *segB; int64_t ldB; int cb; int bcast;
     const float *in_scale, *in_shift; int rows_per_cloud;   // dense: x <- relu(x * scale[cloud] + shift[cloud]) on load (GroupNorm + ReLU of the producer layer)
     int aff_pad;                                // > 0: the tile's scale/shift rows are staged in shared memory (2 * aff_pad floats)
+    float *stats;                               // dense rows: per 32-row block column sums and sums of squares [blocks][2][cout_total] (GroupNorm statistics of the OUTPUT), or null
     int wstage_bytes, bias_floats, region_cols, tmem_cols, nst_log2;
     int nsplit, last_npad, cout_total;          // single wide layer split into 256-column chunks over grid.y
     int f16, small;
@@ -910,12 +911,18 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                         for (int q = 0; q < 4; ++q)
                             *reinterpret_cast<float4 *>(stg(lane * 64 + ((q ^ (lane >> 1)) & 3) * 16)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
                         __syncwarp();
+                        float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int R = (lane >> 2) + 8 * i, q = lane & 3;
                             const float4 t = *reinterpret_cast<const float4 *>(stg(R * 64 + ((q ^ (R >> 1)) & 3) * 16));
                             const int64_t orow = row0 + R;
                             const int c = c0 + 4 * q;
+                            if (a.stats && orow < a.rows) {
+                                ssum.x += t.x; ssum.y += t.y; ssum.z += t.z; ssum.w += t.w;
+                                ssq.x = fmaf(t.x, t.x, ssq.x); ssq.y = fmaf(t.y, t.y, ssq.y);
+                                ssq.z = fmaf(t.z, t.z, ssq.z); ssq.w = fmaf(t.w, t.w, ssq.w);
+                            }
                             if (orow < a.rows && c < cout_last) {
                                 float *dst = a.out + orow * a.ldo + col_off + c;
                                 if (vec_ok && c + 4 <= cout_last) {
@@ -926,6 +933,28 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                                     if (c + 2 < cout_last) dst[2] = t.z;
                                     if (c + 3 < cout_last) dst[3] = t.w;
                                 }
+                            }
+                        }
+                        if (a.stats) {
+                            // GroupNorm statistics of this layer's output, fused into its epilogue: column sums over
+                            // the warp's 32 rows (lanes that share q hold the same 4 columns), one plain store per
+                            // (32-row block, column) -- deterministic, no atomics; captra_group_norm_finalize
+                            // combines the blocks of a cloud in fp64
+#pragma unroll
+                            for (int o = 4; o < 32; o <<= 1) {
+                                ssum.x += __shfl_xor_sync(kFull, ssum.x, o); ssum.y += __shfl_xor_sync(kFull, ssum.y, o);
+                                ssum.z += __shfl_xor_sync(kFull, ssum.z, o); ssum.w += __shfl_xor_sync(kFull, ssum.w, o);
+                                ssq.x += __shfl_xor_sync(kFull, ssq.x, o); ssq.y += __shfl_xor_sync(kFull, ssq.y, o);
+                                ssq.z += __shfl_xor_sync(kFull, ssq.z, o); ssq.w += __shfl_xor_sync(kFull, ssq.w, o);
+                            }
+                            const int c = c0 + 4 * lane;             // lanes 0..3 <-> q
+                            if (lane < 4 && c < cout_last) {
+                                const int ccol = col_off - a.col_off + c;                      // column within the layer's output
+                                float *sp = a.stats + (size_t)(row0 >> 5) * 2 * a.cout_total + ccol;
+                                const float vs[4] = {ssum.x, ssum.y, ssum.z, ssum.w}, vq[4] = {ssq.x, ssq.y, ssq.z, ssq.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (c + j < cout_last) { sp[j] = vs[j]; sp[a.cout_total + j] = vq[j]; }
                             }
                         }
                         __syncwarp();                                 // the next chunk reuses the staging tile
@@ -1203,7 +1232,7 @@ int tc_sa_mlp_max_pre(int b, int n, int s, int k, int cpre, const float *xyz, co
 static int tc_point_mlp_ex(int64_t rows, const float *segA, int64_t ldA, int ca, const float *segB, int64_t ldB, int cb,
                            int bcast, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy, int col_off,
                            int group, bool f16, cudaStream_t stream, const float *in_scale, const float *in_shift,
-                           int rows_per_cloud) {
+                           int rows_per_cloud, float *stats = nullptr) {
     CAPTRA_REQUIRE(group == 0 || ((group == 32 || group == 64 || group == 128) && d->relu_last),
                    "point_mlp(tc): grouped max needs group in {32,64,128} and a final ReLU");
     TcArgs a{};
@@ -1214,6 +1243,8 @@ static int tc_point_mlp_ex(int64_t rows, const float *segA, int64_t ldA, int ca,
     a.out = y; a.ldo = ldy; a.col_off = col_off;
     a.segA = segA; a.ldA = ldA; a.ca = ca; a.segB = segB; a.ldB = ldB; a.cb = cb; a.bcast = bcast;
     a.in_scale = in_scale; a.in_shift = in_shift; a.rows_per_cloud = rows_per_cloud;
+    CAPTRA_REQUIRE(stats == nullptr || group == 0, "point_mlp: output statistics need row output (group 0)");
+    a.stats = stats;
     if (in_scale) {
         // a tile must not straddle two clouds: the kernel stages one cloud's scale/shift rows per tile
         CAPTRA_REQUIRE(rows_per_cloud % TC_ROWS == 0, "point_mlp_affine: rows_per_cloud must be a multiple of %d (got %d)", TC_ROWS, rows_per_cloud);
@@ -1310,6 +1341,58 @@ __global__ void __launch_bounds__(256) group_norm_affine_kernel(int npts, int C,
     }
 }
 
+// Second half of the fused GroupNorm statistics: stats [clouds * npts / 32][2][C] holds, per 32-row block, the column
+// sums and sums of squares the producing GEMM's epilogue wrote (TcArgs::stats).  One CTA per (cloud, 32 channels)
+// combines the npts / 32 blocks of its cloud in fp64 and emits the same per-(cloud, channel) affine as
+// group_norm_affine_kernel -- 16 MB of partials instead of a second pass over the 268 MB activation.
+__global__ void __launch_bounds__(256) group_norm_finalize_kernel(int nblk, int npts, int C, int cpg, const float *__restrict__ stats,
+                                                                  const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                  float eps, float *__restrict__ scale, float *__restrict__ shift) {
+    __shared__ double s_sum[8][GN_CB], s_sq[8][GN_CB];
+    const int b = blockIdx.y, cb = blockIdx.x * GN_CB;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = cb + tx;
+    double a = 0, q = 0;
+    if (c < C) {
+        const float *base = stats + (size_t)b * nblk * 2 * C + c;
+        int r = ty;
+        for (; r + 24 < nblk; r += 32) {          // 8 loads in flight per thread
+            float va[4], vq[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                va[u] = __ldg(base + (size_t)(r + 8 * u) * 2 * C);
+                vq[u] = __ldg(base + (size_t)(r + 8 * u) * 2 * C + C);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a += (double)va[u]; q += (double)vq[u]; }
+        }
+        for (; r < nblk; r += 8) {
+            a += (double)__ldg(base + (size_t)r * 2 * C);
+            q += (double)__ldg(base + (size_t)r * 2 * C + C);
+        }
+    }
+    s_sum[ty][tx] = a; s_sq[ty][tx] = q;
+    __syncthreads();
+    if (threadIdx.x < GN_CB) {
+        double a2 = 0, q2 = 0;
+        for (int i = 0; i < 8; ++i) { a2 += s_sum[i][threadIdx.x]; q2 += s_sq[i][threadIdx.x]; }
+        s_sum[0][threadIdx.x] = a2; s_sq[0][threadIdx.x] = q2;
+    }
+    __syncthreads();
+    if (threadIdx.x < GN_CB && c < C) {
+        const int g0 = (threadIdx.x / cpg) * cpg;
+        double a2 = 0, q2 = 0;
+        for (int j = 0; j < cpg; ++j) { a2 += s_sum[0][g0 + j]; q2 += s_sq[0][g0 + j]; }
+        const double n = (double)npts * cpg;
+        const double mean = a2 / n;
+        const double var = fmax(q2 / n - mean * mean, 0.0);
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        const double sc = (gamma ? (double)gamma[c] : 1.0) * rstd;
+        scale[(size_t)b * C + c] = (float)sc;
+        shift[(size_t)b * C + c] = (float)((beta ? (double)beta[c] : 0.0) - mean * sc);
+    }
+}
+
 }  // namespace captra
 
 using namespace captra;
@@ -1329,11 +1412,31 @@ extern "C" int captra_group_norm_affine(int clouds, int npts, int c, int channel
     return CAPTRA_OK;
 }
 
+extern "C" int captra_group_norm_finalize(int clouds, int npts, int c, int channels_per_group, const float *stats,
+                                          const float *gamma, const float *beta, float eps, float *scale, float *shift,
+                                          captra_stream_t stream) {
+    CAPTRA_REQUIRE(clouds >= 0 && npts >= 32 && npts % 32 == 0 && c >= 1, "group_norm_finalize: bad sizes (npts must be a multiple of 32)");
+    CAPTRA_REQUIRE(channels_per_group >= 1 && GN_CB % channels_per_group == 0 && c % channels_per_group == 0,
+                   "group_norm_finalize: channels_per_group must divide %d and C", GN_CB);
+    if (clouds == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(stats && scale && shift, "group_norm_finalize: null pointer");
+    CAPTRA_REQUIRE(clouds <= 65535, "group_norm_finalize: too many clouds");
+    group_norm_finalize_kernel<<<dim3(ceil_div(c, GN_CB), clouds), 256, 0, as_stream(stream)>>>(npts / 32, npts, c, channels_per_group, stats,
+                                                                                           gamma, beta, eps, scale, shift);
+    CAPTRA_CHECK_LAUNCH("group_norm_finalize");
+    return CAPTRA_OK;
+}
+
 namespace captra {
 int tc_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale, const float *in_shift,
                         int rows_per_cloud, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
                         int col_off, bool f16, cudaStream_t stream) {
     return tc_point_mlp_ex(rows, x, ldx, cin, nullptr, 0, 0, 0, d, packed, y, ldy, col_off, 0, f16, stream, in_scale, in_shift, rows_per_cloud);
+}
+int tc_point_mlp_gnstats(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale, const float *in_shift,
+                         int rows_per_cloud, const captra_mlp_desc *d, const void *packed, float *y, int64_t ldy,
+                         int col_off, float *stats, bool f16, cudaStream_t stream) {
+    return tc_point_mlp_ex(rows, x, ldx, cin, nullptr, 0, 0, 0, d, packed, y, ldy, col_off, 0, f16, stream, in_scale, in_shift, rows_per_cloud, stats);
 }
 }  // namespace captra
 

@@ -204,6 +204,42 @@ class PackedMLP:
         return out
 
 
+    def rows_stats(self, x, scale, shift, rows_per_cloud, out=None):
+        """rows_affine (scale / shift may be None: plain input) that also returns the per-32-row-block column
+        sums / sums of squares of its OUTPUT (captra_point_mlp_gnstats), which group_norm_finalize turns into the
+        next GroupNorm's affine -- the activation is not read a second time for its statistics."""
+        f32 = torch.float32
+        impl = self._pick(self.impl)
+        if impl not in (1, 2) or self._layers is not None:
+            raise _lib.CaptraError("rows_stats needs a chain the fused tcgen05 kernel supports")
+        R, cin = x.shape
+        if out is None:
+            out = torch.empty(R, self.cout, dtype=f32, device=self.device)
+        stats = torch.empty(((R + 127) // 128) * 4, 2, self.cout, dtype=f32, device=self.device)
+        _lib.call("point_mlp[R=%d,C=%d->%s,g=0,impl=%d,%sstats]" % (R, self.cin, "-".join(map(str, self.couts)), impl,
+                                                                   "affine," if scale is not None else ""),
+                  _lib.load().captra_point_mlp_gnstats, R, _lib.ptr(x, f32, "x"), x.stride(0), cin,
+                  _lib.ptr(scale, f32, "scale") if scale is not None else None,
+                  _lib.ptr(shift, f32, "shift") if shift is not None else None, rows_per_cloud,
+                  ctypes.byref(self.desc), self._pack(impl).data_ptr(), _lib.ptr(out, f32, "out"), out.shape[-1], 0,
+                  stats.data_ptr(), impl, _lib.stream_ptr(self.device), device=self.device)
+        return out, stats
+
+
+def group_norm_finalize(stats, clouds, npts, gn):
+    """Per-(cloud, channel) scale/shift of `gn` from the block statistics written by PackedMLP.rows_stats."""
+    C = stats.shape[2]
+    scale = torch.empty(clouds, C, dtype=torch.float32, device=stats.device)
+    shift = torch.empty_like(scale)
+    f32 = torch.float32
+    _lib.call("group_norm_finalize[B=%d,n=%d,C=%d]" % (clouds, npts, C), _lib.load().captra_group_norm_finalize,
+              clouds, npts, C, C // gn.num_groups, stats.data_ptr(),
+              gn.weight.detach().contiguous().data_ptr() if gn.weight is not None else None,
+              gn.bias.detach().contiguous().data_ptr() if gn.bias is not None else None,
+              float(gn.eps), scale.data_ptr(), shift.data_ptr(), _lib.stream_ptr(stats.device), device=stats.device)
+    return scale, shift
+
+
 def group_norm_affine(y, clouds, npts, gn):
     """Per-(cloud, channel) scale/shift equivalent to `gn` (torch.nn.GroupNorm) applied to the pre-norm
     activation y [clouds*npts, C] (point-major): GroupNorm(y) == y * scale + shift."""

@@ -11,13 +11,15 @@ under autograd the torch modules run, exactly as in the reference.  One exact sa
 reference evaluates all P rotation heads on all B*P canonicalised clouds and keeps the diagonal
 (networks.py:200-203); head p is evaluated only on part p's copy here, which yields the same tensors.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from . import mlp as _mlp
 from .backbones import PointNet2Msg
-from .mlp import PackedMLP, fold_conv_bn, group_norm_affine
+from .mlp import PackedMLP, fold_conv_bn, group_norm_affine, group_norm_finalize
 from .pointnet_utils import _FusedCache, _needs_autograd
 from .pose_utils.pose_fit import part_fit_st_no_ransac
 
@@ -120,10 +122,22 @@ class MLPConv1d(nn.Module):
             self._cache = _FusedCache()
         packs = self._cache.get(self, lambda: [PackedMLP([c.weight.detach().reshape(c.out_channels, c.in_channels)],
                                                          [c.bias.detach()], relu_last=False, impl=_mlp.DEFAULT_IMPL) for c in convs])
-        y = packs[0].rows(feat_pm.reshape(B * N, C))
+        x = feat_pm.reshape(B * N, C)
+        if N % 128 != 0 or os.environ.get("CAPTRA_GN_FUSED", "1") == "0":     # unfused statistics pass (odd cloud sizes; A/B knob)
+            y = packs[0].rows(x)
+            for i in range(1, len(convs)):
+                scale, shift = group_norm_affine(y, B, N, gns[i - 1])
+                y = packs[i].rows_affine(y, scale, shift, N)
+            return y.view(B, N, -1)
+        # the statistics of a layer's output are taken in that layer's epilogue (rows_stats) and finalised on
+        # 16 MB of block partials, so an activation is written once and read once
+        y, stats = packs[0].rows_stats(x, None, None, N)
         for i in range(1, len(convs)):
-            scale, shift = group_norm_affine(y, B, N, gns[i - 1])
-            y = packs[i].rows_affine(y, scale, shift, N)
+            scale, shift = group_norm_finalize(stats, B, N, gns[i - 1])
+            if i < len(convs) - 1:
+                y, stats = packs[i].rows_stats(y, scale, shift, N)
+            else:
+                y = packs[i].rows_affine(y, scale, shift, N)
         return y.view(B, N, -1)
 
 

@@ -198,6 +198,18 @@ int captra_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, 
                             const void *packed, float *y, int64_t ldy, int col_off, int impl,
                             captra_stream_t stream);
 
+/* The same launch with the GroupNorm statistics of its OUTPUT fused into the epilogue (in_scale / in_shift may be
+ * NULL: plain input).  stats [ceil(rows/128)*4][2][cout] receives, per 32-row block, the column sums and sums of
+ * squares of y; captra_group_norm_finalize turns the blocks of each cloud into the per-(cloud, channel) affine of
+ * the following GroupNorm -- the activation is never re-read for its statistics.  Deterministic (no atomics). */
+int captra_point_mlp_gnstats(int64_t rows, const float *x, int64_t ldx, int cin, const float *in_scale,
+                             const float *in_shift, int rows_per_cloud, const captra_mlp_desc *mlp,
+                             const void *packed, float *y, int64_t ldy, int col_off, float *stats, int impl,
+                             captra_stream_t stream);
+int captra_group_norm_finalize(int clouds, int npts, int c, int channels_per_group, const float *stats,
+                               const float *gamma, const float *beta, float eps, float *scale, float *shift,
+                               captra_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * 4. Pose fit (pose_utils/procrustes.py, pose_utils/pose_fit.py) -- Python in the reference,
  *    with torch.svd on the CPU (procrustes.py:27-30,170-174); here on the device.

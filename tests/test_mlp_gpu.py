@@ -289,3 +289,31 @@ def test_group_norm_affine_kernel(cuda):
         got = y.view(B, N, C) * scale.view(B, 1, C) + shift.view(B, 1, C)
         want = gn(y.view(B, N, C).transpose(1, 2)).transpose(1, 2)
         torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("clouds,npts,cin,cout,affine", [(3, 256, 128, 512, False), (2, 384, 512, 256, True), (5, 128, 64, 72, True)])
+def test_group_norm_statistics_fused_in_epilogue(impl, clouds, npts, cin, cout, affine, cuda):
+    """captra_point_mlp_gnstats + captra_group_norm_finalize: the per-(cloud, channel) GroupNorm affine taken from
+    the producing GEMM's epilogue must equal the one computed by the separate statistics pass over its output."""
+    from captra_b200.mlp import PackedMLP, group_norm_affine, group_norm_finalize
+    gen = torch.Generator().manual_seed(clouds * npts + cout)
+    R = clouds * npts
+    x = torch.randn(R, cin, generator=gen).to(cuda)
+    ws, bs = _rand_mlp(cin, [cout], gen, cuda)
+    gn = torch.nn.GroupNorm(cout // 2, cout).to(cuda)
+    with torch.no_grad():
+        gn.weight.copy_(torch.rand(cout, generator=gen) + 0.5)
+        gn.bias.copy_(torch.randn(cout, generator=gen) * 0.1)
+    mlp = PackedMLP(ws, bs, relu_last=False, impl=impl)
+    sc = (torch.rand(clouds, cin, generator=gen) + 0.5).to(cuda) if affine else None
+    sh = (torch.randn(clouds, cin, generator=gen) * 0.2).to(cuda) if affine else None
+    y, stats = mlp.rows_stats(x, sc, sh, npts)
+    want_y = mlp.rows_affine(x, sc, sh, npts) if affine else mlp.rows(x)
+    torch.testing.assert_close(y, want_y, rtol=0, atol=0)                 # same kernel, same numbers
+    s1, t1 = group_norm_finalize(stats, clouds, npts, gn)
+    s0, t0 = group_norm_affine(y, clouds, npts, gn)
+    torch.testing.assert_close(s1, s0, rtol=2e-5, atol=1e-6)
+    torch.testing.assert_close(t1, t0, rtol=2e-5, atol=2e-6)
+    ref = gn(want_y.view(clouds, npts, cout).transpose(1, 2)).transpose(1, 2).reshape(R, cout)
+    torch.testing.assert_close(y * s1.repeat_interleave(npts, 0) + t1.repeat_interleave(npts, 0), ref, rtol=1e-4, atol=1e-4)
