@@ -257,7 +257,7 @@ struct TcPiece {
 // or 2 (3xTF32) producer groups, one CTA per SM.  SMALL (every layer <= 128 columns: the sa1 scales,
 // fp1): 4-chunk slabs, G = 2 / 1, 64 KB and 256 TMEM columns per CTA so TWO CTAs share an SM and one
 // tile's epilogue overlaps the other's MMAs.
-template <int MODE, bool F16, bool SMALL, int NSTL2>  // MODE 0: SA gather loader, 1: dense-row loader; 2^NSTL2 pipeline stages; the last epilogue is chosen by a.group
+template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING>  // MODE 0: SA gather loader, 1: dense-row loader; 2^NSTL2 pipeline stages; RING: SA layer 0 (<= 8 channels) comes entirely from the metadata ring; the last epilogue is chosen by a.group
 __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_kernel(const TcArgs a) {
     constexpr int G = tc_groups(F16, SMALL);
     constexpr int PROD = 128 * G;                  // producer / epilogue threads (warps 0 .. 4G-1)
@@ -416,7 +416,8 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
         // of two L2 round trips (1300 + ~2000 cycles per tile before; sa1 has 1-slab layer 0s).
         uint32_t it = 0, tcnt = 0;
         const int glog2 = a.group > 0 ? __ffs(a.group) - 1 : 0;
-        const bool l0_small = MODE == 0 && a.cin0 <= 8 && a.cfeat <= 4;
+        // (the LARGE shape keeps this a run-time flag: its register allocation is better with the branch in place)
+        const bool l0_small = SMALL ? RING : (MODE == 0 && a.cin0 <= 8 && a.cfeat <= 4);
         int m_idx[4];
         int m_pnt[4];
         float m_xyz[4][3], m_cen[4][3], m_f[4][4];
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
             bool valid;
             const float *pa, *pb;             // rows of the two input segments
         };
-        const bool l0_small = MODE == 0 && a.cin0 <= 8 && a.cfeat <= 4;   // SA layer 0 entirely inside the metadata ring
+        const bool l0_small = SMALL ? RING : (MODE == 0 && a.cin0 <= 8 && a.cfeat <= 4);   // SA layer 0 entirely inside the metadata ring (compile-time for the SMALL shape: the gather code is not built into the sa1 launches)
         uint32_t tcnt = 0;                    // this CTA's running tile count (metadata ring slot and parity)
 
         auto warp_wait = [&](uint64_t *bar, uint32_t parity) {   // one lane polls, the warp follows
@@ -834,7 +835,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 TC_STAMP(30);
                 const float inv = bias_s[bias_off + npad];   // 1 / weight scale of the last layer
                 const float *bl = bias_s + bias_off;
-                if (a.group > 0) {
+                if (MODE == 0 || a.group > 0) {    // (SA launches always reduce: the row-major epilogue is not compiled into them)
                     // Transposed accumulator: TMEM lane = output channel (block cb, lane r), column = tile
                     // row (point).  Group g reduces the columns [g*SEG, (g+1)*SEG) of every channel block,
                     // 32 columns (one smallest centroid group) at a time: a per-thread max of the raw
@@ -1153,9 +1154,10 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool
     return CAPTRA_OK;
 }
 
-template <int MODE, bool F16, bool SMALL, int NSTL2>
+template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING = false>
 static int tc_launch_t(TcArgs &a, size_t smem, cudaStream_t stream) {
-    auto kern = mlp_tc_kernel<MODE, F16, SMALL, NSTL2>;
+    if (MODE == 0 && SMALL && !RING && a.cin0 <= 8 && a.cfeat <= 4 && !a.pre_pad) return tc_launch_t<MODE, F16, SMALL, NSTL2, MODE == 0 && SMALL>(a, smem, stream);
+    auto kern = mlp_tc_kernel<MODE, F16, SMALL, NSTL2, RING>;
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
