@@ -257,7 +257,7 @@ struct TcPiece {
 // or 2 (3xTF32) producer groups, one CTA per SM.  SMALL (every layer <= 128 columns: the sa1 scales,
 // fp1): 4-chunk slabs, G = 2 / 1, 64 KB and 256 TMEM columns per CTA so TWO CTAs share an SM and one
 // tile's epilogue overlaps the other's MMAs.
-template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING>  // MODE 0: SA gather loader, 1: dense-row loader; 2^NSTL2 pipeline stages; RING: SA layer 0 (<= 8 channels) comes entirely from the metadata ring; the last epilogue is chosen by a.group
+template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING, bool GRP>  // GRP: grouped-max epilogue (always for SA), else row output; MODE 0: SA gather loader, 1: dense-row loader; 2^NSTL2 pipeline stages; RING: SA layer 0 (<= 8 channels) comes entirely from the metadata ring; the last epilogue is chosen by a.group
 __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_kernel(const TcArgs a) {
     constexpr int G = tc_groups(F16, SMALL);
     constexpr int PROD = 128 * G;                  // producer / epilogue threads (warps 0 .. 4G-1)
@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 TC_STAMP(30);
                 const float inv = bias_s[bias_off + npad];   // 1 / weight scale of the last layer
                 const float *bl = bias_s + bias_off;
-                if (MODE == 0 || a.group > 0) {    // (SA launches always reduce: the row-major epilogue is not compiled into them)
+                if (GRP) {    // compile-time: each launch carries only the epilogue it runs
                     // Transposed accumulator: TMEM lane = output channel (block cb, lane r), column = tile
                     // row (point).  Group g reduces the columns [g*SEG, (g+1)*SEG) of every channel block,
                     // 32 columns (one smallest centroid group) at a time: a per-thread max of the raw
@@ -1154,10 +1154,11 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool
     return CAPTRA_OK;
 }
 
-template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING = false>
+template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING = false, bool GRP = (MODE == 0)>
 static int tc_launch_t(TcArgs &a, size_t smem, cudaStream_t stream) {
-    if (MODE == 0 && SMALL && !RING && a.cin0 <= 8 && a.cfeat <= 4 && !a.pre_pad) return tc_launch_t<MODE, F16, SMALL, NSTL2, MODE == 0 && SMALL>(a, smem, stream);
-    auto kern = mlp_tc_kernel<MODE, F16, SMALL, NSTL2, RING>;
+    if (MODE == 0 && SMALL && !RING && a.cin0 <= 8 && a.cfeat <= 4 && !a.pre_pad) return tc_launch_t<MODE, F16, SMALL, NSTL2, MODE == 0 && SMALL, true>(a, smem, stream);
+    if (MODE == 1 && !GRP && a.group > 0) return tc_launch_t<MODE, F16, SMALL, NSTL2, false, true>(a, smem, stream);
+    auto kern = mlp_tc_kernel<MODE, F16, SMALL, NSTL2, RING, GRP>;
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
