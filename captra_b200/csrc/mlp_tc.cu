@@ -257,7 +257,7 @@ struct TcPiece {
 // or 2 (3xTF32) producer groups, one CTA per SM.  SMALL (every layer <= 128 columns: the sa1 scales,
 // fp1): 4-chunk slabs, G = 2 / 1, 64 KB and 256 TMEM columns per CTA so TWO CTAs share an SM and one
 // tile's epilogue overlaps the other's MMAs.
-template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING, bool GRP>  // GRP: grouped-max epilogue (always for SA), else row output; MODE 0: SA gather loader, 1: dense-row loader; 2^NSTL2 pipeline stages; RING: SA layer 0 (<= 8 channels) comes entirely from the metadata ring; the last epilogue is chosen by a.group
+template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING, bool GRP, bool GN>  // GRP: grouped-max epilogue (always for SA), else row output; GN: GroupNorm head launch (affine on load and / or output statistics); MODE 0: SA gather loader, 1: dense-row loader; 2^NSTL2 pipeline stages; RING: SA layer 0 (<= 8 channels) comes entirely from the metadata ring; the last epilogue is chosen by a.group
 __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_kernel(const TcArgs a) {
     constexpr int G = tc_groups(F16, SMALL);
     constexpr int PROD = 128 * G;                  // producer / epilogue threads (warps 0 .. 4G-1)
@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
             // SA: this tile's slot of the metadata ring (filled by the TMA warp during the previous tile)
             const float4 *mrow = meta_s + ((size_t)(tcnt & 1) * TC_ROWS + warp * ROWS_W + lrow) * 2;
             if (MODE == 0) warp_wait(&meta_full[tcnt & 1], (tcnt >> 1) & 1);
-            if (MODE == 1 && a.in_scale) {
+            if (MODE == 1 && GN && a.in_scale) {
                 // a tile lies inside one cloud (rows_per_cloud % 128 == 0, checked on the host): stage the
                 // cloud's scale/shift rows (GroupNorm + ReLU of the producer layer) in shared memory
                 const int cloud = (int)((tile * TC_ROWS) / a.rows_per_cloud);
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
             };
             // GroupNorm + ReLU of the producer layer, applied to a loaded unit (dense mode)
             auto affine_unit = [&](const RowMeta &m, int c0, float (&x)[8]) {
-                if (MODE != 1 || !a.in_scale || !m.valid || c0 >= a.cin0) return;
+                if (MODE != 1 || !GN || !a.in_scale || !m.valid || c0 >= a.cin0) return;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const float4 sc = *reinterpret_cast<const float4 *>(aff_s + c0 + 4 * q);
@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                             const float4 t = *reinterpret_cast<const float4 *>(stg(R * 64 + ((q ^ (R >> 1)) & 3) * 16));
                             const int64_t orow = row0 + R;
                             const int c = c0 + 4 * q;
-                            if (a.stats && orow < a.rows) {
+                            if (GN && a.stats && orow < a.rows) {
                                 ssum.x += t.x; ssum.y += t.y; ssum.z += t.z; ssum.w += t.w;
                                 ssq.x = fmaf(t.x, t.x, ssq.x); ssq.y = fmaf(t.y, t.y, ssq.y);
                                 ssq.z = fmaf(t.z, t.z, ssq.z); ssq.w = fmaf(t.w, t.w, ssq.w);
@@ -936,7 +936,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                                 }
                             }
                         }
-                        if (a.stats) {
+                        if (GN && a.stats) {
                             // GroupNorm statistics of this layer's output, fused into its epilogue: column sums over
                             // the warp's 32 rows (lanes that share q hold the same 4 columns), one plain store per
                             // (32-row block, column) -- deterministic, no atomics; captra_group_norm_finalize
@@ -1154,11 +1154,12 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool
     return CAPTRA_OK;
 }
 
-template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING = false, bool GRP = (MODE == 0)>
+template <int MODE, bool F16, bool SMALL, int NSTL2, bool RING = false, bool GRP = (MODE == 0), bool GN = false>
 static int tc_launch_t(TcArgs &a, size_t smem, cudaStream_t stream) {
     if (MODE == 0 && SMALL && !RING && a.cin0 <= 8 && a.cfeat <= 4 && !a.pre_pad) return tc_launch_t<MODE, F16, SMALL, NSTL2, MODE == 0 && SMALL, true>(a, smem, stream);
     if (MODE == 1 && !GRP && a.group > 0) return tc_launch_t<MODE, F16, SMALL, NSTL2, false, true>(a, smem, stream);
-    auto kern = mlp_tc_kernel<MODE, F16, SMALL, NSTL2, RING, GRP>;
+    if (MODE == 1 && !GRP && !GN && (a.in_scale || a.stats)) return tc_launch_t<MODE, F16, SMALL, NSTL2, false, false, MODE == 1>(a, smem, stream);
+    auto kern = mlp_tc_kernel<MODE, F16, SMALL, NSTL2, RING, GRP, GN>;
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     a.ntiles = ceil_div<int64_t>(a.rows, TC_ROWS);
