@@ -1,6 +1,6 @@
-// mlp_tc.cu -- fused shared per-point MLP on the 5th-gen tensor cores (impl 1): tcgen05.mma with
-// TMEM accumulators, operands staged in shared memory (weights by bulk-copy TMA), 3xTF32 split
-// arithmetic so the result matches true fp32 to ~1e-6 (the reference's convs are true fp32;
+// mlp_tc.cu -- fused shared per-point MLP on the 5th-gen tensor cores (impl 1, 2): tcgen05.mma with
+// TMEM accumulators, operands staged in shared memory (weights by bulk-copy TMA), 3-term split
+// arithmetic (3xTF32 or fp16x3) so the result matches true fp32 to ~1e-6 (the reference's convs are true fp32;
 // single-pass TF32 misses the 1e-4 pose tolerance, SURVEY section 7 "hard parts").
 #include "mlp_common.cuh"
 #include "tc_common.cuh"
@@ -94,31 +94,41 @@ __global__ void __launch_bounds__(128) umma_debug_gemm_kernel(int K, int N, cons
 
 
 // ------------------------------------------------------------------------------------------------
-// The fused kernel (v6: piece-parallel producers).
+// The fused kernel.
 //
-// Persistent CTAs walk 128-row tiles.  A K slab is KC = 16*G input channels; producer group g
-// (128 threads: thread r <-> tile row r <-> TMEM lane r) owns the 16-channel PIECE g of EVERY slab, so
-// all 4G producer warps work on the same slab at once: the per-slab latency is one piece, the
+// Persistent CTAs walk 128-row tiles.  A K slab is KC = 16*G input channels; for layers > 0 producer
+// group g (128 threads: thread r <-> tile row r <-> TMEM lane r) owns the 16-channel PIECE g of EVERY
+// slab, so all 4G producer warps work on the same slab at once: the per-slab latency is one piece, the
 // pipeline restarts quickly at a layer boundary, and 16 (LARGE) / 2x8 (SMALL, two CTAs per SM) warps
-// give the SM enough independent instruction streams to hide the TMEM / L2 / conversion latencies
-// (v5 had 8 warps alternating whole slabs and ran at 0.16 IPC per scheduler, profiles/r01_*).
+// give the SM enough independent instruction streams to hide the TMEM / L2 / conversion latencies.
 //
 //   layer l, K slab s, stage st = slab counter mod NST:
-//     producers   : piece g of the A slab -> (hi, lo) planes of a_stage[st]
-//         layer 0 : gathered from global through the index list (SA) or row pointers (dense), with a
-//                   two-slab register prefetch so the L2 gather latency hides behind the MMAs
+//     producers   : the A slab -> (hi, lo) planes of a_stage[st]
+//         layer 0 : rows dealt out per WARP for coalesced reads (8 rows x 128 contiguous bytes per LDG.256
+//                   instruction), gathered through the metadata ring (SA) or row pointers (dense), one slab
+//                   ahead in registers (two at 168 registers); optional on-load transforms: GroupNorm
+//                   affine + ReLU of the producer layer (heads), or the projected layer 0 of an SA scale
+//                   (relu(P[j] + W_x (x_j - c) + b), tc_sa_mlp_max_pre)
 //         layer>0 : read straight out of TMEM -- 16 accumulator columns of layer l-1 ARE piece g of
 //                   slab s of layer l -- + bias, ReLU, split.  The epilogue of layer l-1 and the MMAs
 //                   of layer l overlap slab by slab; accumulators ping-pong between two TMEM regions
 //                   and no activation ever touches shared memory in fp32.
-//     TMA thread  : W slab (hi plane | lo plane, pre-split, chunk-major in global) -> w_stage[st]
-//     MMA thread  : k-steps x 3 terms (lo*hi, hi*lo, hi*hi) of tcgen05.mma, tcgen05.commit ->
+//     TMA warp    : W slab (hi plane | lo plane, pre-split, chunk-major in global) -> w_stage[st]; for SA
+//                   launches it also resolves the NEXT tile's gather metadata (index -> point ->
+//                   coordinates) into a two-tile shared-memory ring while it waits for free stages
+//     MMA warp    : k-steps x 3 terms (lo*hi, hi*lo, hi*hi) of tcgen05.mma, tcgen05.commit ->
 //                   empty[st]; after a layer's last slab also -> d_ready.  K-steps (and pieces) that
 //                   only carry zero padding are skipped in every layer.
-//   last epilogue : group > 0 -> max over the rows of each group on the RAW accumulators (bias and
-//                                ReLU commute with the max: one fma + max per column instead of per
-//                                element), one coalesced row write per group
-//                   group = 0 -> the thread's row straight to global (point-major)
+//   last epilogue : grouped (GRP) -> the last layer is computed TRANSPOSED (channels in TMEM lanes), so the
+//                                max over a group's rows is a per-thread reduction of the RAW accumulators
+//                                (bias and ReLU commute with the max), one coalesced row write per group
+//                   rows        -> the warp's 32 x 16 block is transposed through the idle A stages and
+//                                written as 8 rows x 64 contiguous bytes per store; optionally the column
+//                                sums / sums of squares of the block (GroupNorm statistics of the output)
+//
+// The template parameters select exactly the code a launch runs (loader, operand type, CTA shape, stages,
+// ring-only layer 0, epilogue kind, GroupNorm-head extras): at 96 registers per thread every dead branch
+// costs spills, and with the L1 carved out for shared memory a spill is an L2 round trip.
 //
 // Shared-memory operand layout (K-major, no swizzle): element (row, k) of a slab lives at
 //   plane + (k / EPC) * ROWS*16 + row*16 + (k % EPC) * sizeof  (EPC = 8 halfs or 4 tf32 per 16-byte
@@ -732,8 +742,27 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 }
             };
             TC_STAMP(1);
-            // ---------------- layer 0: coalesced gather, two slabs ahead ----------------
-            {
+            // ---------------- layer 0 ----------------
+            if constexpr (RING) {
+                // <= 8 input channels: one slab, the row comes assembled from the metadata ring (straight-line code:
+                // no prefetch buffers, no loops -- these launches are instruction-issue bound)
+                const int kstore = (a.kreal[0] + KMMA - 1) / KMMA * KMMA;
+                acquire(it);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c0 = 8 * unit_idx(u);
+                    if (c0 < kstore && !(a.dbg & 1)) {
+                        float x[8];
+                        load_unit(RS == 2 ? u : 0, c0, x);
+                        uint32_t hi[F16 ? 4 : 8], lo[F16 ? 4 : 8];
+                        convert_unit(x, hi, lo);
+                        store_unit(it, unit_row(u), unit_idx(u), hi, lo);
+                    }
+                }
+                release(it);
+                ++it;
+            } else {
+                // coalesced gather, one or two slabs ahead
                 const int nslab = a.kpad[0] / KC;
                 const int kstore = (a.kreal[0] + KMMA - 1) / KMMA * KMMA;   // channels the MMA k-steps read
                 // prefetch distance: two slabs where the register budget allows (3xTF32 LARGE: 168), else one (96)
