@@ -166,6 +166,10 @@ def setup_dist(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION (this pool's default); the contract is one
+        # JSON line there.  An explicit INFO / TRACE request is left alone.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
