@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 const int nslab = a.kpad[0] / KC;
                 const int kstore = (a.kreal[0] + KMMA - 1) / KMMA * KMMA;   // channels the MMA k-steps read
                 // prefetch distance: two slabs where the register budget allows (3xTF32 LARGE: 168), else one (96)
-#ifdef CAPTRA_TC_PF2      // A/B build knob (scripts/ab_build.sh)
+#ifdef CAPTRA_TC_PF2      // A/B build knob: CAPTRA_EXTRA_NVCC_FLAGS=-DCAPTRA_TC_PF2 CAPTRA_LIB_OUT=... python -m captra_b200.build
                 constexpr int PF = SMALL ? 1 : 2;
 #else
                 constexpr int PF = (SMALL || F16) ? 1 : 2;
