@@ -245,13 +245,24 @@ __device__ __forceinline__ float warp_colmax16(const float (&x)[16], int lane, i
     return v;
 }
 
+// The timing probes (knock-out knobs and phase stamps, CAPTRA_TC_DBG) are compiled in only with -DCAPTRA_TC_PROBES:
+//   CAPTRA_EXTRA_NVCC_FLAGS=-DCAPTRA_TC_PROBES CAPTRA_LIB_OUT=captra_b200/libcaptra_ops_probes.so python -m captra_b200.build
+//   CAPTRA_LIB_PATH=$PWD/captra_b200/libcaptra_ops_probes.so python scripts/tc_probe.py
+// In the product library they are constant-folded away: the run-time tests sat in the per-slab loops of launches
+// that are instruction-issue bound.
+#ifdef CAPTRA_TC_PROBES
+#define TC_DBG (a.dbg)
+#else
+#define TC_DBG 0
+#endif
+
 // timing probe (CAPTRA_TC_DBG bit 32): producer thread 0 of CTA 0 stamps clock64() at phase
 // boundaries of its first tiles; read back with captra_debug_tc_timestamps
 __device__ long long g_tc_ts[512];
 __device__ int g_tc_ts_n;
 #define TC_STAMP(code)                                                              \
     do {                                                                            \
-        if ((a.dbg & 32) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {       \
+        if ((TC_DBG & 32) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {       \
             const int i__ = g_tc_ts_n;                                              \
             if (i__ < 255) { g_tc_ts[2 * i__] = clock64(); g_tc_ts[2 * i__ + 1] = (code); g_tc_ts_n = i__ + 1; } \
         }                                                                           \
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                             // the max over a centroid's points is a per-thread reduction in the epilogue.
     #pragma unroll
                             for (int j = 0; j < KSTEPS; ++j) {
-                                if (j >= nks || (a.dbg & 4)) break;
+                                if (j >= nks || (TC_DBG & 4)) break;
                                 for (uint32_t cb = 0; cb < nblk; ++cb) {
                                     const uint32_t dT = tmem_d + cb * 128u;
                                     const uint64_t wo = (uint64_t)(cb * 128u);        // 128 rows * 16 bytes, in 16-byte units
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                         } else {
     #pragma unroll
                             for (int j = 0; j < KSTEPS; ++j) {
-                                if (j >= nks || (a.dbg & 4)) break;
+                                if (j >= nks || (TC_DBG & 4)) break;
                                 if (F16) {
                                     umma_f16(tmem_d, al, bh, idesc, (s | j) ? 1u : 0u);
                                     umma_f16(tmem_d, ah, bl, idesc, 1u);
@@ -500,7 +511,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                     const uint32_t st = it & (NST - 1), ph = (it >> nst_log2) & 1;
                     mbar_wait_warp_relaxed(&empty[st], ph ^ 1);
                     if (elect_one()) {
-                        if (a.dbg & 2) {
+                        if (TC_DBG & 2) {
                             mbar_arrive(&full[st]);
                         } else {
                             mbar_arrive_expect_tx(&full[st], bytes);
@@ -571,7 +582,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
         auto release = [&](uint32_t i) {      // hand the filled stage to the MMA thread
             // every writer fences its own generic-proxy stores towards the async proxy; one elected
             // lane per warp then arrives
-            if (!(a.dbg & 8)) fence_proxy_async_smem();
+            if (!(TC_DBG & 8)) fence_proxy_async_smem();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[i & (NST - 1)]);
@@ -668,7 +679,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
             auto load_unit = [&](int ri, int c0, float (&x)[8]) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] = 0.f;
-                if (c0 >= a.cin0 || (a.dbg & 65)) return;             // padding channels (probes: no gather)
+                if (c0 >= a.cin0 || (TC_DBG & 65)) return;             // padding channels (probes: no gather)
                 const float *pa = nullptr, *pb = nullptr;
                 float dx = 0.f, dy = 0.f, dz = 0.f;
                 if (MODE == 0) {
@@ -751,7 +762,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int c0 = 8 * unit_idx(u);
-                    if (c0 < kstore && !(a.dbg & 1)) {
+                    if (c0 < kstore && !(TC_DBG & 1)) {
                         float x[8];
                         load_unit(RS == 2 ? u : 0, c0, x);
                         uint32_t hi[F16 ? 4 : 8], lo[F16 ? 4 : 8];
@@ -781,7 +792,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int c0 = s * KC + 8 * unit_idx(u);
-                        if (c0 < kstore && !(a.dbg & 1)) {        // else: pure padding, the MMA thread skips these k-steps
+                        if (c0 < kstore && !(TC_DBG & 1)) {        // else: pure padding, the MMA thread skips these k-steps
                             uint32_t hi[F16 ? 4 : 8], lo[F16 ? 4 : 8];
                             affine_unit(meta[RS == 2 ? u : 0], c0, buf[u]);
                             convert_unit(buf[u], hi, lo);
@@ -823,10 +834,10 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 tcgen05_fence_after();
                 TC_STAMP(10 + l);
                 uint32_t v[16];
-                if (cg < kreal && !(a.dbg & 129)) tmem_ld_32x16(tsrc, v);
+                if (cg < kreal && !(TC_DBG & 129)) tmem_ld_32x16(tsrc, v);
                 for (int s = 0; s < nslab; ++s, ++it) {
                     const int c0 = s * KC + cg;
-                    const bool active = c0 < kreal && !(a.dbg & 1);
+                    const bool active = c0 < kreal && !(TC_DBG & 1);
                     TcPiece<F16> p;
                     if (active) {
                         tmem_ld_wait();
@@ -843,7 +854,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                         // before it, so the compiler does not copy v to keep the old values alive)
 #pragma unroll
                         for (int j = 0; j < 16; ++j) asm volatile("" : "+f"(x[j]));
-                        if (s + 1 < nslab && c0 + KC < kreal && !(a.dbg & 128)) tmem_ld_32x16(tsrc + (uint32_t)((s + 1) * KC), v);
+                        if (s + 1 < nslab && c0 + KC < kreal && !(TC_DBG & 128)) tmem_ld_32x16(tsrc + (uint32_t)((s + 1) * KC), v);
                         convert(x, std::true_type{}, p);
                     }
                     acquire(it);

@@ -1,6 +1,7 @@
 """Timing probe for the fused tcgen05 MLP kernel: the SA scales and dense-row shapes of cfg2, each
 timed alone (PROBE_IMPL = 1 | 2; PROBE_STAMPS=1 prints the clock64 phase stamps of a build made with
-CAPTRA_TC_DBG bit 32); PROBE_DBG=0,2,4,... times the knock-out knobs."""
+CAPTRA_TC_DBG bit 32); PROBE_DBG=0,2,4,... times the knock-out knobs.  The knobs and stamps exist only in the probes
+build of the library (-DCAPTRA_TC_PROBES, see csrc/mlp_tc.cu): select it with CAPTRA_LIB_PATH; the product library ignores them."""
 import os
 import sys
 import time
