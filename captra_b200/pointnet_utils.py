@@ -117,6 +117,17 @@ def _pm(t):
     return t.transpose(1, 2).contiguous()
 
 
+def split_first_layer(W0, b0, n_feat):
+    """Split the BN-folded first layer of an SA scale, y = W0 [features | x - c] + b0 (the reference concatenates
+    the grouped features first, then the centred coordinates: pointnet_utils.py:239-241), into the per-point part
+    and the per-(centroid, sample) part of captra_sa_mlp_max_pre:
+        Wf  [c1, n_feat]  -- applied once per point:  P[j] = Wf f_j
+        tab [4, c1]       -- rows wx, wy, wz, bias:   y = P[j] + wx dx + wy dy + wz dz + bias."""
+    Wf = W0[:, :n_feat]
+    tab = torch.cat([W0[:, n_feat:n_feat + 3].t(), b0[None, :]], 0).contiguous()
+    return Wf, tab
+
+
 class PointNetSetAbstractionMsg(nn.Module):
     """pointnet_utils.py:191-250."""
 
@@ -175,10 +186,10 @@ class PointNetSetAbstractionMsg(nn.Module):
                 tail = PackedMLP([w for w, _ in wb[1:]], [b for _, b in wb[1:]], relu_last=True)
                 if tail._layers is not None or not tail._tc_supported():
                     return None
-                tab = torch.cat([W0[:, D:D + 3].t(), b0[None, :]], 0).contiguous()      # [4, c1]: wx, wy, wz, bias
+                tab = split_first_layer(W0, b0, D)[1]                                   # [4, c1]: wx, wy, wz, bias
                 scales.append((tail, tab, off, W0.shape[0]))
                 off += W0.shape[0]
-            Wf = torch.cat([wb[0][0][:, :D] for wb in folded], 0).contiguous()           # [sum c1, D]
+            Wf = torch.cat([split_first_layer(wb[0][0], wb[0][1], D)[0] for wb in folded], 0).contiguous()   # [sum c1, D]
             proj = PackedMLP([Wf], [torch.zeros(Wf.shape[0], device=Wf.device)], relu_last=False)
             return proj, scales
         return self._cache_pre.get(self, build)
