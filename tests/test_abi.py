@@ -94,3 +94,33 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libcaptra_ops.so")
     with pytest.raises(_lib.CaptraError):
         _lib.load()
+
+
+def test_mlp_pack_bytes_is_host_only_and_shape_dispatch():
+    """captra_mlp_pack_bytes is pure host arithmetic (no GPU needed): the fused tcgen05 layouts accept the chains
+    the tracker keeps on chip and refuse (-1) the ones it runs layer by layer; the exact-fp32 layout takes all."""
+    import ctypes
+    from captra_b200 import _lib
+    from captra_b200.mlp import MlpDesc
+    L = _lib.load()
+
+    def desc(cin, couts):
+        d = MlpDesc()
+        d.nlayers, d.cin, d.relu_last = len(couts), cin, 1
+        for i, c in enumerate(couts):
+            d.cout[i] = c
+        return d
+
+    fused = [(6, [64, 96, 128]), (3, [32, 32, 64]), (323, [128, 196, 256]), (128, [196, 256]), (134, [128, 128, 128]), (512, [512])]
+    for cin, couts in fused:
+        for impl in (0, 1, 2):
+            n = L.captra_mlp_pack_bytes(ctypes.byref(desc(cin, couts)), impl)
+            assert n > 0 and n % 4 == 0, (cin, couts, impl, n)
+    # the fp16 pack holds two 2-byte planes per weight, the tf32 pack two 4-byte planes
+    d = desc(323, [128, 196, 256])
+    assert L.captra_mlp_pack_bytes(ctypes.byref(d), 2) < L.captra_mlp_pack_bytes(ctypes.byref(d), 1)
+    # sa3 (515 -> 256 -> 512 -> 1024): a layer wider than 256 columns inside a chain is not fused on the tensor cores
+    d = desc(515, [256, 512, 1024])
+    assert L.captra_mlp_pack_bytes(ctypes.byref(d), 1) == -1 and L.captra_mlp_pack_bytes(ctypes.byref(d), 2) == -1
+    assert L.captra_mlp_pack_bytes(ctypes.byref(d), 0) > 0
+    assert L.captra_mlp_pack_bytes(ctypes.byref(d), 7) == -1
