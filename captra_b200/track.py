@@ -24,11 +24,19 @@ def default_pointnet_cfg():
 
 
 CATEGORIES = {
-    # configs/obj_config/obj_info_nocs.yml:6-20 (bottle; bowl/can identical) and
-    # obj_info_sapien.yml:52-65 (laptop); network section of config_track.yml:33-37
+    # the six NOCS-REAL275 categories, configs/obj_config/obj_info_nocs.yml:7-127 (one rigid part each, extra_dims 1
+    # = one background class; `sym` per category :9,25,40,79,95,111) -- one checkpoint pair per category,
+    # scripts/track/nocs/1_bottle.sh ... 6_mug.sh
     "bottle": dict(num_parts=1, sym=True, tree=[-1], extra_dims=1),
+    "bowl": dict(num_parts=1, sym=True, tree=[-1], extra_dims=1),
+    "camera": dict(num_parts=1, sym=False, tree=[-1], extra_dims=1),
+    "can": dict(num_parts=1, sym=True, tree=[-1], extra_dims=1),
+    "nocs_laptop": dict(num_parts=1, sym=False, tree=[-1], extra_dims=1),
+    "mug": dict(num_parts=1, sym=False, tree=[-1], extra_dims=1),
+    # SAPIEN articulated laptop, obj_info_sapien.yml:52-65 (two parts, no background class)
     "laptop": dict(num_parts=2, sym=False, tree=[-1, 0], extra_dims=0),
 }
+NOCS_CATEGORIES = ("bottle", "bowl", "camera", "can", "nocs_laptop", "mug")     # obj_category 1..6
 
 
 def make_cfg(category="bottle", device="cuda:0"):
@@ -42,20 +50,95 @@ def make_cfg(category="bottle", device="cuda:0"):
 
 
 def init_weights(module, seed=0):
-    """Reference init (trainer.py:111: xavier, gain sqrt(2)) + randomised BN running stats so the
-    folded-BN path is exercised.  Deterministic for a given torch build."""
-    gen = torch.Generator().manual_seed(seed)
-    for m in module.modules():
-        if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d)):
-            fan_in = m.in_channels
-            fan_out = m.out_channels
-            std = (2.0 ** 0.5) * (2.0 / (fan_in + fan_out)) ** 0.5
-            m.weight.data.copy_(torch.randn(m.weight.shape, generator=gen) * std)
-            m.bias.data.zero_()
-        elif isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
-            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
-            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) + 0.5)
+    """Reference init (trainer.py:18-37,111 with weight_init: xavier -- xavier_normal_, gain sqrt(2), zero bias, on
+    every Conv*/Linear*; norm layers keep their defaults) + randomised BatchNorm running statistics so the
+    folded-BN path is exercised.  Every tensor is drawn from its own generator seeded by
+    (seed, state-dict key), so any module with the same state-dict keys and shapes -- the reference's own
+    CoordNet / PartCanonNet (tests/golden/make_golden.py) or this package's mirrors -- gets bit-identical
+    values, independent of module registration order.  Deterministic for a given torch build."""
+    import zlib
+    mods = dict(module.named_modules())
+
+    def gen(key):
+        return torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) % (2 ** 31))
+    with torch.no_grad():
+        for name, m in mods.items():
+            pre = name + "." if name else ""
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d, torch.nn.Linear)):
+                fan_in = m.weight.shape[1] * (m.weight[0, 0].numel() if m.weight.dim() > 2 else 1)
+                fan_out = m.weight.shape[0] * (m.weight[0, 0].numel() if m.weight.dim() > 2 else 1)
+                std = (2.0 ** 0.5) * (2.0 / (fan_in + fan_out)) ** 0.5
+                m.weight.copy_(torch.randn(m.weight.shape, generator=gen(pre + "weight")) * std)
+                if m.bias is not None:
+                    m.bias.zero_()
+            elif isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen(pre + "running_mean")) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen(pre + "running_var")) + 0.5)
     return module
+
+
+def make_trained_like(coordnet, num_parts):
+    """Synthetic stand-in for a TRAINED CoordNet (there are no checkpoints offline).  Random weights give NOCS
+    predictions uncorrelated with the cloud, and the scale fit then is a small difference of large sums: any
+    1e-5 feature noise shows up as 1e-3 on the scale.  A trained CoordNet predicts NOCS ~ canonical coordinates
+    and a segmentation that follows the geometry, so route the canonicalised xyz (skip connection of fp1,
+    backbones.py:67) through to the heads: channel i carries relu(x_i), channel 3+i relu(-x_i); the NOCS head
+    outputs sigmoid(4 x_i + 0.05 * (random deep features)) - 0.5; the segmentation splits the parts along x
+    (P > 1) and calls |x| > 0.3 background (extra class).  Works on the reference's CoordNet and on this
+    package's mirror alike (same attribute names)."""
+    bb = coordnet.backbone
+    with torch.no_grad():
+        def passthrough(conv, bn, first=False):
+            w = conv.weight
+            w[:6] = 0
+            if first:
+                for i in range(3):
+                    w[i, i] = 1.0
+                    w[3 + i, i] = -1.0
+            else:
+                for i in range(6):
+                    w[i, i] = 1.0
+            conv.bias[:6] = 0
+            if bn is not None:
+                bn.weight[:6] = 1.0
+                bn.bias[:6] = 0
+                bn.running_mean[:6] = 0
+                bn.running_var[:6] = 1.0 - bn.eps
+        passthrough(bb.fp1.mlp_convs[0], bb.fp1.mlp_bns[0], first=True)
+        passthrough(bb.fp1.mlp_convs[1], bb.fp1.mlp_bns[1])
+        passthrough(bb.conv1, bb.bn1)
+        passthrough(coordnet.nocs_head[0], coordnet.nocs_head[1])
+        last = coordnet.nocs_head[3]
+        last.weight.mul_(0.05)
+        last.bias.zero_()
+        for p in range(num_parts):
+            for i in range(3):
+                last.weight[3 * p + i, :6] = 0
+                last.weight[3 * p + i, i] = 4.0
+                last.weight[3 * p + i, 3 + i] = -4.0
+        seg = coordnet.seg_head[0]
+        seg.weight.mul_(0.05)
+        seg.bias.zero_()
+        seg.weight[:, :6] = 0
+        for p in range(num_parts):                    # parts: slabs along x
+            c = (p + 0.5) / num_parts - 0.5           # slab centre in [-0.5, 0.5]
+            seg.weight[p, 0], seg.weight[p, 3] = 16.0 * c, -16.0 * c
+            seg.bias[p] = -8.0 * c * c
+        if seg.weight.shape[0] > num_parts:           # background: |x| > 0.3
+            seg.weight[num_parts, 0] = seg.weight[num_parts, 3] = 8.0
+            seg.bias[num_parts] = -2.4
+    return coordnet
+
+
+def state_dict_digest(module):
+    """sha256 over the float tensors of a state dict in key order (pins init_weights across machines)."""
+    import hashlib
+    h = hashlib.sha256()
+    for k, v in sorted(module.state_dict().items()):
+        if v.is_floating_point():
+            h.update(k.encode())
+            h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
 
 
 class Tracker(torch.nn.Module):
@@ -70,9 +153,10 @@ class Tracker(torch.nn.Module):
         self.root = [p for p in range(self.num_parts) if cfg["obj_tree"][p] == -1][0]
 
     @torch.no_grad()
-    def step(self, points, points_mean, last_pose):
+    def step(self, points, points_mean, last_pose, want_pred=False):
         """model.py:454-476.  points [B,3,N] (mean-subtracted), points_mean [B,3,1],
-        last_pose {'rotation' [B,P,3,3], 'translation' [B,P,3,1], 'scale' [B,P]} -> new pose dict."""
+        last_pose {'rotation' [B,P,3,3], 'translation' [B,P,3,1], 'scale' [B,P]} -> new pose dict
+        (with want_pred: (pose, {'seg','nocs','labels','points'}), the CoordNet predictions of this frame)."""
         canon = {k: last_pose[k][:, self.root] for k in ("rotation", "translation", "scale")}
         # With one rigid part both networks see the cloud canonicalised by the same pose
         # (networks.py:38-41 vs :184-187), so FPS picks, ball-query lists and 3-NN weights -- functions
@@ -84,6 +168,8 @@ class Tracker(torch.nn.Module):
         pred_labels = torch.max(pred["seg"], dim=-2)[1]
         out = self.net({"points": points, "points_mean": points_mean, "state": {"part": last_pose},
                         "pred_labels": pred_labels, "pred_nocs": pred_npcs, "geom": geom}, test_mode=True)
+        if want_pred:
+            return out["part"], {"seg": pred["seg"], "nocs": pred["nocs"], "labels": pred_labels, "points": pred["points"]}
         return out["part"]
 
 
@@ -126,12 +212,13 @@ def synthetic_track_batch(b, category="bottle", n=4096, seed=0):
     c = CATEGORIES[category]
     P = c["num_parts"]
     case = synthetic.pose_fit_case(b, P, n, seed=seed, sym=False)
-    rng = np.random.default_rng(seed + 1)
     cam = case["cam"]                                  # [b,n,3]
     mean = cam.mean(1, keepdims=True)
     points = np.ascontiguousarray(np.swapaxes(cam - mean, 1, 2)).astype(np.float32)
     R = case["R"].copy()
+    t, s = case["t"].copy(), case["s"].copy()
     for bi in range(b):
+        rng = np.random.default_rng([seed + 1, bi])    # per trajectory: cloud i is the same whatever the batch size
         for pi in range(P):
             axis = rng.normal(size=3)
             axis /= np.linalg.norm(axis)
@@ -139,10 +226,8 @@ def synthetic_track_batch(b, category="bottle", n=4096, seed=0):
             K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
             dR = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
             R[bi, pi] = R[bi, pi] @ dR
-    pose = {
-        "rotation": R.astype(np.float32),
-        "translation": (case["t"] + rng.normal(scale=0.03, size=case["t"].shape))[..., None].astype(np.float32),
-        "scale": (case["s"] + rng.normal(scale=0.02, size=case["s"].shape)).astype(np.float32),
-    }
+            t[bi, pi] += rng.normal(scale=0.03, size=3)
+            s[bi, pi] += rng.normal(scale=0.02)
+    pose = {"rotation": R.astype(np.float32), "translation": t[..., None].astype(np.float32), "scale": s.astype(np.float32)}
     return {"points": points, "points_mean": np.swapaxes(mean, 1, 2).astype(np.float32), "pose": pose,
             "gt": {"rotation": case["R"], "translation": case["t"][..., None], "scale": case["s"]}}

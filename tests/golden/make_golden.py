@@ -165,7 +165,87 @@ def golden_backbone():
     print("backbone.npz", len(out), "arrays")
 
 
+def _install_index_shims():
+    """The reference's index-producing shims -> CUDA-kernel semantics via oracle/cpu_ref (module docstring)."""
+    import pointnet_utils as PU
+    PU.farthest_point_sample = lambda xyz, npoint: T(cpu_ref.furthest_point_sample(xyz.contiguous().numpy(), npoint)).long()
+    PU.query_ball_point = lambda radius, nsample, xyz, new_xyz: T(
+        cpu_ref.ball_query(radius, nsample, xyz.contiguous().numpy(), new_xyz.contiguous().numpy())).long()
+
+    def three_nn(xyz1, xyz2):
+        d, i = cpu_ref.three_nn(xyz1.contiguous().numpy(), xyz2.contiguous().numpy())
+        return T(d), T(i).long()
+    PU.three_nn = three_nn
+
+
+FRAME_CASES = {          # tag -> (category, clouds, weight seed, input seed, trained-like CoordNet heads)
+    "bottle": ("bottle", 2, 0, 0, False),       # the bench's cfg2 tracker (seed 0) on the first two clouds of its batch 0
+    "camera": ("camera", 2, 0, 40, False),      # rigid, non-symmetric: 6-D rotation head, Gram-Schmidt
+    "laptop": ("laptop", 2, 0, 0, False),       # SAPIEN, two parts: per-part canonicalisation, P heads, diagonal
+    # the same with track.make_trained_like applied: mixed labels, NOCS ~ canonical coordinates (well-conditioned fit)
+    "bottle_t": ("bottle", 2, 3, 5, True),
+    "laptop_t": ("laptop", 2, 3, 5, True),
+}
+FEAT_STRIDE = 16      # backbone features are stored for every 16th point (keeps the fixture small)
+
+
+def golden_frame():
+    """One full tracking frame (model.py:454-476) through the REFERENCE's own CoordNet and PartCanonNet
+    (network/models/networks.py:19-110,144-239, blocks.py:146-193, backbones.py, pointnet_utils.py modules,
+    pose_utils/{pose_fit,procrustes,part_dof_utils,rotations}.py), eval mode, at the real
+    pointnet2_camera.yml widths on 4096-point clouds.  Weights: captra_b200.track.init_weights (reference
+    xavier init + randomised BN running stats, keyed by state-dict name) -- NOT stored, regenerated by the
+    tests and pinned by their sha256; inputs: captra_b200.track.synthetic_track_batch (regenerated too,
+    digest stored).  Stored: seg, nocs, labels, canonicalised points, strided backbone features of both
+    networks, per-point rotation head output, rtvec, the final pose."""
+    import hashlib
+    import networks as RN          # the reference's network/models/networks.py
+    from captra_b200 import track
+    _install_index_shims()
+    out = {}
+    for tag, (category, B, wseed, iseed, trained) in FRAME_CASES.items():
+        cfg = track.make_cfg(category, device="cpu")
+        P = cfg["num_parts"]
+        npcs_net = track.init_weights(RN.CoordNet(cfg), wseed).eval()
+        net = track.init_weights(RN.PartCanonNet(cfg), wseed + 1).eval()
+        if trained:
+            track.make_trained_like(npcs_net, P)
+        batch = track.synthetic_track_batch(B, category, n=4096, seed=iseed)
+        pts, mean = T(batch["points"]), T(batch["points_mean"])
+        pose = {k: T(v) for k, v in batch["pose"].items()}
+        root = [p for p in range(P) if cfg["obj_tree"][p] == -1][0]
+        feats = {}
+        h1 = npcs_net.backbone.register_forward_hook(lambda m, i, o: feats.__setitem__("coord", o.detach()))
+        h2 = net.regress_net.encoder.register_forward_hook(lambda m, i, o: feats.__setitem__("rot", o.detach()))
+        with torch.no_grad():
+            # model.py:454-476 (EvalTrackModel.forward loop body), npcs_net then net
+            canon = {k: pose[k][:, root] for k in ("rotation", "translation", "scale")}
+            pred = npcs_net({"points": pts, "points_mean": mean, "canon_pose": canon})
+            pred_labels = torch.max(pred["seg"], dim=-2)[1]
+            pred_npcs = pred["nocs"].reshape(B, P, 3, -1)
+            res = net({"points": pts, "points_mean": mean, "state": {"part": pose}, "pred_labels": pred_labels,
+                       "pred_nocs": pred_npcs}, test_mode=True)
+        h1.remove()
+        h2.remove()
+        out[tag + "/meta"] = np.array([B, wseed, iseed, int(trained)])
+        out[tag + "/input_digest"] = np.frombuffer(hashlib.sha256(batch["points"].tobytes() + batch["pose"]["rotation"].tobytes()).digest(), np.uint8)
+        out[tag + "/coord_sd_digest"] = np.frombuffer(bytes.fromhex(track.state_dict_digest(npcs_net)), np.uint8)
+        out[tag + "/rot_sd_digest"] = np.frombuffer(bytes.fromhex(track.state_dict_digest(net)), np.uint8)
+        out[tag + "/canon_points"] = pred["points"].numpy()
+        out[tag + "/seg"] = pred["seg"].numpy()
+        out[tag + "/nocs"] = pred["nocs"].numpy()
+        out[tag + "/labels"] = pred_labels.numpy().astype(np.int16)
+        out[tag + "/feat_coord"] = feats["coord"][:, :, ::FEAT_STRIDE].contiguous().numpy()
+        out[tag + "/feat_rot"] = feats["rot"][:, :, ::FEAT_STRIDE].contiguous().numpy()
+        out[tag + "/point_rotation"] = res["point_rotation"][..., ::FEAT_STRIDE, :, :].contiguous().numpy()
+        for k in ("rotation", "scale", "translation"):
+            out[tag + "/pose_" + k] = res["part"][k].numpy()
+        print(tag, "labels hist", np.bincount(pred_labels.numpy().ravel()), "scale", res["part"]["scale"].numpy().ravel())
+    np.savez_compressed(os.path.join(HERE, "frame.npz"), **out)
+    print("frame.npz", len(out), "arrays", os.path.getsize(os.path.join(HERE, "frame.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    golden_procrustes()
-    golden_ops_index()
-    golden_backbone()
+    which = sys.argv[1:] or ["procrustes", "ops_index", "backbone", "frame"]
+    for name in which:
+        globals()["golden_" + name]()
