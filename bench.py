@@ -1,23 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- tracking frames/s @ 4096 points on N B200s (BASELINE.json metric).
+"""bench.py -- tracking frames/s @ 4096 points on N B200s + ball_query/group HBM GB/s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one tracking frame for a batch of trajectories (the loop body of
-EvalTrackModel.forward, model.py:409-478): CoordNet forward on B clouds, argmax labels,
-RotationNet forward on B*P canonicalised clouds, fused pose fit.  Workload (config.workload):
-BASELINE.json configs[1] "NOCS bottle, batch 32 x 4096 pts" per GPU; with N GPUs every rank tracks
-its own 32 trajectories (weak scaling, no data-path collective) and the end-of-step pose-error
-scalars are summed with one NCCL all-reduce.
+One "step" = one tracking frame for a batch of trajectories (the loop body of EvalTrackModel.forward,
+model.py:409-478): CoordNet forward on B clouds, argmax labels, RotationNet forward on B*P canonicalised clouds,
+fused pose fit, per-frame pose-error reduction (model.py:523-526) -- all inside one CUDA graph.
 
-value : frames/s with the step's inputs already resident in HBM; per-step CUDA-event pairs on the
-        launching stream, L2 flushed between steps (outside the pairs), max over ranks.
-e2e   : same metric through the public API from HOST buffers: each step copies that step's points /
-        means / poses from pinned host memory, runs Tracker.step, and reads the new poses back.
+Workloads (config.workload):
+  cfg2 (default)  BASELINE.json configs[1]: NOCS bottle, 32 x 4096 pts per GPU, weak scaling (every rank tracks its own
+                  32 trajectories; no data-path collective).
+  cfg3            configs[2]: SAPIEN laptop, 2 parts, 16 x 4096 pts per GPU.
+  cfg4            configs[3]: 256 trajectories, category = index mod 6 (six weight sets), contiguous shards over the
+                  ranks, grouped by category inside a rank; STRONG scaling (256 fixed).
+  cfg5            configs[4]: ball_query + group_points on B=64 x 16384 pts, K=64, four SA levels: HBM GB/s vs peak.
+The end-of-batch loss reduction is ONE NCCL all-reduce of the accumulated per-category eval sums after the
+K timed frames (inside the last step's event pair), not one per frame.
+
+value : frames/s with the step's inputs already resident in HBM; per-step CUDA-event pairs on the launching stream,
+        L2 flushed between steps (outside the pairs), max over ranks.
+e2e   : same metric through the public API from HOST buffers: each step copies that step's points / means / poses
+        from pinned host memory, replays the frame, and reads the new poses back before the next frame starts.
 roofline / kernels : a separate profiled pass brackets every C-ABI launch with CUDA events.
-cpu_baseline : oracle/frame_ref (CPU restatement in the reference's structure, "port") timed on this
-        host's cores on a bounded sample.  --impl reference prints the same measurement as its own line.
+query_group : the cfg5 four-level ball_query + group figure (short pass, also in the default line).
+reference_gpu : the REFERENCE's own kernels (oracle/_ref/libpointnet2_ref.so, compiled from its sources) timed per op
+        on the same GPU and shapes next to this library's ("kernel to beat").
+cpu_baseline / --impl reference : the reference's own torch CPU path (oracle/_ref/pyref, copied unmodified by
+        oracle/Makefile; kind "reference") -- or, if that copy is absent, the CPU port oracle/frame_ref (kind "port") --
+        timed on this host's cores on a bounded sample.
 """
 import argparse
 import json
@@ -28,20 +39,36 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-# stdout carries exactly one JSON line: keep NCCL's version/info banner off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+_REFERENCE_ARM = "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:sys.argv.index("--impl") + 2] == ["reference"] \
+    or "--impl=reference" in sys.argv
+if _REFERENCE_ARM:
+    # the reference decides CUDA vs CPU at import time (pointnet_utils.py:8); its CPU path is what this arm times
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+# stdout carries exactly one JSON line.  NCCL prints its banner on stdout at NCCL_DEBUG=VERSION (this pool's default):
+# quiet that, but leave an explicit INFO / TRACE request alone and only move its log to stderr.
+_nd = os.environ.get("NCCL_DEBUG", "").upper()
+if _nd in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
+elif "NCCL_DEBUG_FILE" not in os.environ:
+    os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 WORKLOADS = {
-    "cfg2": dict(category="bottle", batch=32, desc="NOCS-REAL275 rigid (bottle, sym), batch 32 x 4096 pts, full track step"),
-    "cfg3": dict(category="laptop", batch=16, desc="SAPIEN articulated (laptop, 2 parts), batch 16 x 4096 pts, full track step"),
+    "cfg2": dict(categories=["bottle"], batch=32, scaling="weak",
+                 desc="NOCS-REAL275 rigid (bottle, sym), batch 32 x 4096 pts per GPU, full track step"),
+    "cfg3": dict(categories=["laptop"], batch=16, scaling="weak",
+                 desc="SAPIEN articulated (laptop, 2 parts), batch 16 x 4096 pts per GPU, full track step"),
+    "cfg4": dict(categories=None, batch=256, scaling="strong",
+                 desc="NOCS mixed 6-category batch, 256 x 4096 pts total (category = index mod 6, six weight sets), sharded over the GPUs"),
+    "cfg5": dict(categories=None, batch=64, scaling="weak",
+                 desc="dense stress: ball_query + group_points, B=64 x 16384 pts, K=64, 4 SA levels (4096/1024/256/64 centroids, r=.05/.1/.2/.4)"),
 }
 METRIC = "tracking frames/sec @4096 pts"
 UNIT = "frames/s"
+PYREF = os.path.join(ROOT, "oracle", "_ref", "pyref")
 
 
 def peaks():
@@ -53,7 +80,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from before the warm-up to the end of the timed regions."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -102,6 +129,11 @@ def _parse(tag):
     return name, kv
 
 
+def _mlp_shape(kv):
+    cin, widths = kv["C"].split("->")
+    return int(cin), [int(w) for w in widths.split("-")]
+
+
 def algorithmic(tag):
     """(bytes, flops) per launch; the batch size is part of the tag."""
     name, kv = _parse(tag)
@@ -116,35 +148,23 @@ def algorithmic(tag):
     if name == "three_nn_interpolate":
         n, m, C = int(kv["n"]), int(kv["m"]), int(kv["C"])
         return 12 * B * (n + m) + 4 * B * C * m + 4 * B * C * n, 8 * B * n * m + 6 * B * C * n
-    if name == "sa_mlp_max":
+    if name in ("sa_mlp_max", "sa_mlp_max_pre"):
+        # sa_mlp_max_pre: layer 0 was projected per point (a point_mlp launch of its own); this launch gathers the
+        # cin-wide projected rows, adds the 3 coordinate MACs per channel and runs layers 1..: only the MACs executed
+        # here are counted
         N, S, K = int(kv["N"]), int(kv["S"]), int(kv["K"])
-        cin, widths = kv["C"].split("->")
-        cin, widths = int(cin), [int(w) for w in widths.split("-")]
+        cin, widths = _mlp_shape(kv)
         rows = B * S * K
-        macs, last = 0, cin
+        macs, last = (3 * cin if name == "sa_mlp_max_pre" else 0), cin
         for w in widths:
             macs += last * w
             last = w
         wbytes = 4 * sum(a * b for a, b in zip([cin] + widths[:-1], widths))
-        # compulsory traffic of the fused query-group-MLP-max: xyz + features once, idx, output, weights
-        return 12 * B * (N + S) + 4 * B * (cin - 3) * N + 4 * B * S * K + 4 * B * S * widths[-1] + wbytes, 2 * rows * macs
-    if name == "sa_mlp_max_pre":
-        # layer 0 projected per point: this launch gathers cpre-wide projected rows and runs layers 1.. (the
-        # projection itself is a point_mlp launch of its own); only the MACs executed here are counted
-        N, S, K = int(kv["N"]), int(kv["S"]), int(kv["K"])
-        cin, widths = kv["C"].split("->")
-        cin, widths = int(cin), [int(w) for w in widths.split("-")]
-        rows = B * S * K
-        macs, last = 3 * cin, cin
-        for w in widths:
-            macs += last * w
-            last = w
-        wbytes = 4 * sum(a * b for a, b in zip([cin] + widths[:-1], widths))
-        return 12 * B * (N + S) + 4 * B * cin * N + 4 * B * S * K + 4 * B * S * widths[-1] + wbytes, 2 * rows * macs
+        feat = cin if name == "sa_mlp_max_pre" else cin - 3
+        return 12 * B * (N + S) + 4 * B * feat * N + 4 * B * S * K + 4 * B * S * widths[-1] + wbytes, 2 * rows * macs
     if name == "point_mlp":
         R, g = int(kv["R"]), int(kv["g"])
-        cin, widths = kv["C"].split("->")
-        cin, widths = int(cin), [int(w) for w in widths.split("-")]
+        cin, widths = _mlp_shape(kv)
         macs, last = 0, cin
         for w in widths:
             macs += last * w
@@ -154,8 +174,16 @@ def algorithmic(tag):
         return 4 * R * cin + 4 * out_rows * widths[-1] + wbytes, 2 * R * macs
     if name == "part_fit_st":
         P, N = int(kv["P"]), int(kv["N"])
-        nb = B
-        return 2 * 12 * nb * P * N + 8 * nb * N + 52 * nb * P, 60 * nb * P * N
+        return 2 * 12 * B * P * N + 8 * B * N + 52 * B * P, 60 * B * P * N
+    if name == "canonicalize":
+        P, N = int(kv["P"]), int(kv["N"])
+        return 12 * B * N + 12 * B * P * N * 4, 20 * B * P * N
+    if name == "coord_head_post":
+        N, S, C = int(kv["N"]), int(kv["S"]), int(kv["C"])
+        return 4 * B * N * (2 * S + 2 * C) + 8 * B * N, 20 * B * N * (S + C)
+    if name == "rot_head_post":
+        P, N, D = int(kv["P"]), int(kv["N"]), int(kv["D"])
+        return 4 * B * P * N * D + 8 * B * N, 60 * B * P * N
     return 0, 0
 
 
@@ -166,57 +194,173 @@ def setup_dist(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION (this pool's default); the contract is one
-        # JSON line there.  An explicit INFO / TRACE request is left alone.
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
 
 
-def host_batches(workload, rank, nbatch):
-    from captra_b200 import track
+def rank_plan(workload, rank, world):
+    """-> list of (category, count) for this rank, in the order the rank's batch is laid out."""
+    from captra_b200 import shard, track
     w = WORKLOADS[workload]
-    out = []
-    for i in range(nbatch):
-        b = track.synthetic_track_batch(w["batch"], w["category"], n=4096, seed=1000 * rank + i)
-        out.append(b)
-    return out
+    if workload == "cfg4":
+        a, b = shard.shard_range(w["batch"], world, rank)                    # contiguous shard of the 256 trajectories
+        cats = [shard.category_of(i) for i in range(a, b)]                   # category = global index mod 6
+        _, names = track.group_by_category(cats)                             # grouped by category inside the rank
+        plan = []
+        for n in names:
+            if plan and plan[-1][0] == n:
+                plan[-1][1] += 1
+            else:
+                plan.append([n, 1])
+        return [(c, k) for c, k in plan]
+    return [(w["categories"][0], w["batch"])]
+
+
+def host_batch(plan, seed):
+    """Synthetic host inputs of one frame for the rank's plan (numpy float32), concatenated over the categories."""
+    from captra_b200 import track
+    parts = [track.synthetic_track_batch(k, c, n=4096, seed=seed + 17 * j) for j, (c, k) in enumerate(plan)]
+    cat = lambda f: np.concatenate([f(p) for p in parts], 0)
+    return {"points": cat(lambda p: p["points"]), "points_mean": cat(lambda p: p["points_mean"]),
+            "pose": {k: cat(lambda p: p["pose"][k]) for k in parts[0]["pose"]},
+            "gt": {k: cat(lambda p: np.asarray(p["gt"][k], dtype=np.float32)) for k in parts[0]["gt"]}}
 
 
 def pin(a):
     return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 
 
+# --------------------------------------------------------------------------------------------
+# CPU arm
+# --------------------------------------------------------------------------------------------
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _time_steps(fn, warmup, steps):
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        fn()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return ts
+
+
 def cpu_reference_arm(workload, steps, warmup, sample_clouds):
-    """Times oracle/frame_ref.track_step (CPU port in the reference's structure) with all host threads."""
+    """The reference's CPU implementation of the tracking frame on this host's cores (all threads; plus a 1-thread
+    figure).  kind "reference": the reference's own networks.py / blocks.py / backbones.py / pointnet_utils.py torch
+    fallbacks (CUDA=False, pointnet_utils.py:8) + pose_utils, imported unmodified from oracle/_ref/pyref.  kind
+    "port": oracle/frame_ref.track_step when that copy is not there.  Needs CUDA hidden (see the top of this file)."""
     from captra_b200 import track
-    from oracle import cpu_ref, frame_ref
-    w = WORKLOADS[workload]
+    w = WORKLOADS[workload if workload in ("cfg2", "cfg3") else "cfg2"]
+    category = w["categories"][0]
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cpu_ref.set_num_threads(cores)
-    cfg = track.make_cfg(w["category"], device="cpu")
-    trk = track.Tracker(cfg, seed=0).eval()
-    sd_c = {k: v.detach() for k, v in trk.npcs_net.state_dict().items()}
-    sd_r = {k: v.detach() for k, v in trk.net.state_dict().items()}
-    b = track.synthetic_track_batch(sample_clouds, w["category"], n=4096, seed=0)
+    cfg = track.make_cfg(category, device="cpu")
+    P = cfg["num_parts"]
+    b = track.synthetic_track_batch(sample_clouds, category, n=4096, seed=0)
     pts, mean = torch.from_numpy(b["points"]), torch.from_numpy(b["points_mean"])
     pose = {k: torch.from_numpy(v) for k, v in b["pose"].items()}
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            frame_ref.track_step(sd_c, sd_r, cfg, pts, mean, pose)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-    total = float(np.sum(times))
-    return {"value": sample_clouds * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d of %d clouds per step x %d steps (%d warm-up), oracle/frame_ref.track_step, torch %d threads + OpenMP %d" % (
-                sample_clouds, w["batch"], len(times), warmup, cores, cpu_ref.num_threads()),
-            "ms_per_step": 1e3 * total / len(times), "median_ms": 1e3 * float(np.median(times)), "best_ms": 1e3 * float(np.min(times))}
+    per_op = None
+    if os.path.isdir(PYREF) and not torch.cuda.is_available():
+        kind = "reference"
+        sys.path[:0] = [os.path.join(PYREF, "network", "models"), os.path.join(PYREF, "pose_utils"), PYREF]
+        import networks as RN                     # the reference's own modules
+        import pointnet_utils as RPU
+        assert not RPU.CUDA
+        npcs_net = track.init_weights(RN.CoordNet(cfg), 0).eval()
+        net = track.init_weights(RN.PartCanonNet(cfg), 1).eval()
+        root = [p for p in range(P) if cfg["obj_tree"][p] == -1][0]
+
+        def frame(pts, mean, pose):
+            with torch.no_grad():             # model.py:454-476
+                S = pts.shape[0]
+                canon = {k: pose[k][:, root] for k in ("rotation", "translation", "scale")}
+                pred = npcs_net({"points": pts, "points_mean": mean, "canon_pose": canon})
+                labels = torch.max(pred["seg"], dim=-2)[1]
+                return net({"points": pts, "points_mean": mean, "state": {"part": pose}, "pred_labels": labels,
+                            "pred_nocs": pred["nocs"].reshape(S, P, 3, -1)}, test_mode=True)["part"]
+
+        def per_op_ms():
+            """One cloud, all threads: the reference's torch fallbacks of the named ops at the sa1 / fp1 shapes."""
+            x = pts[:1].transpose(1, 2).contiguous()
+            out = {}
+
+            def t(name, fn):
+                fn()
+                t0 = time.perf_counter()
+                r = fn()
+                out[name] = 1e3 * (time.perf_counter() - t0)
+                return r
+            with torch.no_grad():
+                idx = t("farthest_point_sample[4096->512]", lambda: RPU.farthest_point_sample(x, 512))
+                ctr = RPU.index_points(x, idx)
+                g = t("query_ball_point[r=.2,K=128]", lambda: RPU.query_ball_point(0.2, 128, x, ctr))
+                t("group_operation[C=3,K=128]", lambda: RPU.group_operation(x.transpose(1, 2).contiguous(), g))
+                d, i3 = t("three_nn[4096x512]", lambda: RPU.three_nn(x, ctr))
+                f = torch.randn(1, 128, 512)
+                t("three_interpolate[C=128]", lambda: RPU.three_interpolate(f, i3, torch.softmax(-d, -1)))
+                import pose_fit as RPF
+                lab = torch.zeros(1, 4096, dtype=torch.long)
+                src = torch.rand(1, P, 4096, 3) - 0.5
+                t("part_fit_st_no_ransac", lambda: RPF.part_fit_st_no_ransac(lab, src, src * 0.3 + 1.0, pose["rotation"][:1],
+                                                                          {"num_parts": P, "sym": cfg["obj_sym"]}))
+            return out
+    else:
+        kind = "port"
+        from oracle import cpu_ref, frame_ref
+        cpu_ref.set_num_threads(cores)
+        trk = track.Tracker(cfg, seed=0).eval()
+        sd_c = {k: v.detach() for k, v in trk.npcs_net.state_dict().items()}
+        sd_r = {k: v.detach() for k, v in trk.net.state_dict().items()}
+
+        def frame(pts, mean, pose):
+            with torch.no_grad():
+                return frame_ref.track_step(sd_c, sd_r, cfg, pts, mean, pose)[0]
+        per_op_ms = None
+
+    torch.set_num_threads(cores)
+    ts = _time_steps(lambda: frame(pts, mean, pose), warmup, steps)
+    if per_op_ms is not None:
+        per_op = per_op_ms()
+    # 1-thread figure on a smaller sample (bounded: ~10 s)
+    one = min(2, sample_clouds)
+    torch.set_num_threads(1)
+    if kind == "port":
+        cpu_ref.set_num_threads(1)
+    sl = lambda d: {k: v[:one] for k, v in d.items()}
+    t1 = _time_steps(lambda: frame(pts[:one], mean[:one], sl(pose)), 1, 2)
+    torch.set_num_threads(cores)
+    total = float(np.sum(ts))
+    return {"value": sample_clouds * len(ts) / total, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d of %d clouds per step x %d steps (%d warm-up), %s, torch %d threads; 1-thread figure on %d clouds x 2 steps" % (
+                sample_clouds, w["batch"], len(ts), warmup,
+                "the reference's own CoordNet + PartCanonNet torch CPU path (oracle/_ref/pyref)" if kind == "reference" else "oracle/frame_ref.track_step",
+                cores, one),
+            "ms_per_step": 1e3 * total / len(ts), "median_ms": 1e3 * float(np.median(ts)), "best_ms": 1e3 * float(np.min(ts)),
+            "frames_per_s_median": sample_clouds / float(np.median(ts)), "frames_per_s_best": sample_clouds / float(np.min(ts)),
+            "frames_per_s_1thread": one / float(np.median(t1)), "cpu_model": cpu_model_name(), "per_op_ms_1cloud": per_op,
+            "category": category}
+
+
+def cpu_arm_subprocess(workload, sample):
+    """Run the CPU arm in its own process with the GPU hidden (the reference picks its CPU path at import time)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                              "--steps", "5", "--warmup", "1", "--cpu-sample", str(sample)],
+                             env=env, capture_output=True, text=True, timeout=600)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:  # noqa: BLE001
+        return {"error": "cpu arm failed: %s" % str(e)[:200]}
 
 
 def ncu_traffic(tag):
@@ -231,6 +375,111 @@ def ncu_traffic(tag):
     return None if ent is None else ent["dram_bytes_per_launch"]
 
 
+# --------------------------------------------------------------------------------------------
+# cfg5: ball_query + group_points, four SA levels
+# --------------------------------------------------------------------------------------------
+def _timed_us(fn, flush, reps):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return float(np.median(ts))
+
+
+def query_group_pass(dev, flush, B=64, reps=5, cloud="surface"):
+    """BASELINE cfg5 / SURVEY 8d: per level the FUSED ball_query + group of C channels (one call of
+    fused_ops.ball_query_group), algorithmic bytes 12B(N+M) + 4BCN + 4BMK + 4BCMK over its CUDA-event time."""
+    from captra_b200 import fused_ops, synthetic
+    pk = peaks()
+    K = 64
+    if cloud == "uniform":
+        pts = synthetic.batch_uniform(B, 16384, seed=0)
+    else:
+        pts = np.stack([synthetic.surface_box(16384, np.random.default_rng(i))[0] for i in range(B)])
+    cur = torch.from_numpy(pts).to(dev)
+    levels = [(4096, 0.05, 3), (1024, 0.1, 128), (256, 0.2, 256), (64, 0.4, 256)]   # (centroids, radius, channels grouped)
+    out, tot_b, tot_us = [], 0, 0.0
+    for li, (M, r, C) in enumerate(levels):
+        N = cur.shape[1]
+        t_fps = _timed_us(lambda: fused_ops.fps_gather(cur, M), flush, 2)
+        _, ctr = fused_ops.fps_gather(cur, M)
+        feats = cur.transpose(1, 2).contiguous() if C == 3 else torch.randn(B, C, N, device=dev)
+        us = _timed_us(lambda: fused_ops.ball_query_group(r, K, cur, ctr, feats), flush, reps)
+        by = 12 * B * (N + M) + 4 * B * C * N + 4 * B * M * K + 4 * B * C * M * K
+        out.append({"level": li + 1, "N": N, "M": M, "K": K, "radius": r, "C": C, "us": us, "alg_bytes": by,
+                    "gbs": by / us / 1e3, "frac_of_hbm_peak": by / us / 1e3 / pk["hbm"], "fps_us": t_fps})
+        tot_b += by
+        tot_us += us
+        cur = ctr
+        del feats
+    return {"what": "cfg5: ball_query + group_points, 4 SA levels, B=%d x 16384 pts, K=64, %s clouds" % (B, cloud),
+            "alg_bytes": tot_b, "us": tot_us, "gbs": tot_b / tot_us / 1e3, "frac_of_hbm_peak": tot_b / tot_us / 1e3 / pk["hbm"],
+            "peak_gbs": pk["hbm"], "peak_source": pk["src"] + " hbm_gbs", "levels": out}
+
+
+def reference_gpu_pass(dev, flush, B=32):
+    """The reference's own CUDA kernels (oracle/_ref, compiled from its sources for sm_100) vs this library's, per op,
+    same inputs, CUDA events, L2 flushed, median of 5."""
+    from captra_b200 import synthetic
+    from captra_b200.pointnet_lib import pointnet2_utils as ours
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        return {"unavailable": "oracle/_ref/libpointnet2_ref.so not built"}
+    pts = torch.from_numpy(synthetic.batch_surface_box(B, 4096, seed=0)[0]).to(dev)
+    idx = ours.furthest_point_sample(pts, 512)
+    ctr = torch.gather(pts, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+    feats = torch.randn(B, 128, 4096, device=dev)
+    f512 = torch.randn(B, 128, 512, device=dev)
+    gidx = ours.ball_query(0.2, 128, pts, ctr)
+    d, i3 = ours.three_nn(pts, ctr)
+    w3 = torch.softmax(-d, -1).contiguous()
+    rows = []
+
+    def both(name, f_ref, f_ours):
+        a, b = _timed_us(f_ref, flush, 5), _timed_us(f_ours, flush, 5)
+        rows.append({"op": name, "reference_us": a, "ours_us": b, "speedup": a / b})
+    both("furthest_point_sample[B=%d,4096->512]" % B, lambda: ref_cuda.furthest_point_sample(pts, 512), lambda: ours.furthest_point_sample(pts, 512))
+    for r, K in ((0.05, 32), (0.1, 64), (0.2, 128)):
+        both("ball_query[r=%g,K=%d,M=512]" % (r, K), lambda: ref_cuda.ball_query(r, K, pts, ctr), lambda: ours.ball_query(r, K, pts, ctr))
+    both("group_points[C=128,M=512,K=128]", lambda: ref_cuda.grouping_operation(feats, gidx), lambda: ours.grouping_operation(feats, gidx))
+    both("gather_points[C=128,M=512]", lambda: ref_cuda.gather_operation(feats, idx), lambda: ours.gather_operation(feats, idx))
+    both("three_nn[n=4096,m=512]", lambda: ref_cuda.three_nn(pts, ctr), lambda: ours.three_nn(pts, ctr))
+    both("three_interpolate[C=128,m=512,n=4096]", lambda: ref_cuda.three_interpolate(f512, i3, w3), lambda: ours.three_interpolate(f512, i3, w3))
+    return {"what": "reference kernels (network/models/pointnet_lib/src/*_gpu.cu compiled unmodified for sm_100) vs libcaptra_ops.so, same GPU, same inputs",
+            "ops": rows}
+
+
+def svd_pass(dev, flush):
+    """cfg3 'per-part 3x3 SVD timed separately' (procrustes.py:25-56): rotate_pts_batch instances/s on the device kernel
+    and transform_pts_mask(rotation=None) for B=16, P=2 x 4096 pts."""
+    from captra_b200 import synthetic
+    from captra_b200.pose_utils import procrustes as P
+    out = {}
+    for count in (32, 4096, 1 << 20):
+        M = torch.randn(count, 3, 3, device=dev)
+        R = torch.empty_like(M)
+        from captra_b200 import _lib
+        us = _timed_us(lambda: _lib.call("procrustes_rot3[n=%d]" % count, _lib.load().captra_procrustes_rot3, count, M.data_ptr(),
+                                         R.data_ptr(), _lib.stream_ptr(dev), device=dev), flush, 5)
+        out["rot3_%d" % count] = {"us": us, "instances_per_s": count / us * 1e6}
+    case = synthetic.pose_fit_case(16, 2, 4096, seed=0)
+    labels = torch.from_numpy(case["labels"]).to(dev)
+    src = torch.from_numpy(case["nocs"]).to(dev)
+    tgt = torch.from_numpy(case["cam"]).to(dev).unsqueeze(1).expand(-1, 2, -1, -1)
+    eye = torch.cat([torch.eye(2), torch.zeros(2, 2)], 0).to(dev)
+    mask = eye[labels].transpose(-1, -2).unsqueeze(-1)
+    us = _timed_us(lambda: P.transform_pts_mask(src, tgt, mask, mask, rotation=None, sym=False), flush, 5)
+    out["transform_pts_mask[B=16,P=2,N=4096,rotation=None]"] = {"us": us, "fits_per_s": 32 / us * 1e6}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,27 +487,27 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=16, help="clouds per CPU-baseline step (about 10 s of host work for 1 + 5 steps)")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="clouds per CPU-baseline step (about 20-30 s of host work in all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the query_group (cfg5), reference_gpu and svd passes")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--dump-kernels", default=None, help="write the full per-launch table of the profiled pass (JSON) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
-    config = {"workload": w["desc"], "name": args.workload, "points": 4096, "batch_per_gpu": w["batch"],
-              "category": w["category"], "weights": "random init (seeded), BN stats randomised, eval mode"}
+    config = {"workload": w["desc"], "name": args.workload, "points": 4096, "batch": w["batch"],
+              "weights": "reference init (xavier, gain sqrt 2; seeded by state-dict key), BN running stats randomised, eval mode"}
 
     if args.impl == "reference":
-        rank = int(os.environ.get("RANK", "0"))
-        if rank != 0:
+        if int(os.environ.get("RANK", "0")) != 0:
             return 0
-        steps = min(args.steps, 5)
-        r = cpu_reference_arm(args.workload, steps, min(args.warmup, 1), args.cpu_sample)
+        steps, warm = min(args.steps, 5), min(args.warmup, 1)
+        r = cpu_reference_arm(args.workload, steps, warm, args.cpu_sample)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-                "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, cpu_sample="%d clouds per step (frames/s is per cloud, so the sample size does not bias it)" % args.cpu_sample),
+                "cpu_baseline": r, "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
 
@@ -266,42 +515,63 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (the product has no CPU path)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    torch.backends.cuda.matmul.allow_tf32 = False   # heads are torch fp32; keep them true fp32 like the reference
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    from captra_b200 import _lib, mlp, shard, track
+    from captra_b200 import _lib, frame_ops, mlp, shard, track
     _lib.load()
-    cfg = track.make_cfg(w["category"], device=str(dev))
-    trk = track.Tracker(cfg, seed=0).to(dev).eval()
-    B, P = w["batch"], cfg["num_parts"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                     # before the warm-up, so the short timed region is covered
+
+    if args.workload == "cfg5":
+        pk = peaks()
+        qg = query_group_pass(dev, flush, B=w["batch"], reps=max(args.steps, 3))
+        qgu = query_group_pass(dev, flush, B=w["batch"], reps=3, cloud="uniform")
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            l1 = qg["levels"][0]
+            print(json.dumps({"metric": "ball_query+group HBM GB/s vs peak", "value": qg["gbs"], "unit": "GB/s", "n_gpus": world,
+                              "steps": max(args.steps, 3), "warmup": 1, "ms_per_step": qg["us"] * 1e-3, "higher_is_better": True,
+                              "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                              "config": dict(config, l2="flushed between launches"), "clocks": clocks,
+                              "roofline": {"kernel": "ball_query_group level 1", "bound": "hbm", "achieved": l1["gbs"], "peak": pk["hbm"],
+                                           "unit": "GB/s", "frac": l1["frac_of_hbm_peak"], "traffic": None, "peak_source": pk["src"] + " hbm_gbs"},
+                              "query_group": qg, "query_group_uniform": qgu, "gpu_launches": int(_lib.launch_count())}))
+        return 0
+
+    plan = rank_plan(args.workload, rank, world)
+    Bn = sum(k for _, k in plan)
+    if len(plan) == 1:
+        trk = track.Tracker(track.make_cfg(plan[0][0], device=str(dev)), seed=0).to(dev).eval()
+    else:
+        trk = track.MixedTracker([c for c, k in plan for _ in range(k)], device=dev, seed=0).to(dev).eval()
+    P = trk.num_parts
 
     nb = 4  # distinct host batches, cycled
-    hb = host_batches(args.workload, rank, nb)
+    hb = [host_batch(plan, seed=1000 * rank + i) for i in range(nb)]
     pinned = [dict(points=pin(b["points"]), mean=pin(b["points_mean"]), pose={k: pin(v) for k, v in b["pose"].items()},
                    gt={k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(dev) for k, v in b["gt"].items()}) for b in hb]
     resident = [dict(points=p["points"].to(dev), mean=p["mean"].to(dev), pose={k: v.to(dev) for k, v in p["pose"].items()}) for p in pinned]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    def loss_scalars(pose, gt):
-        """pose-error sums a tracker logs per batch (test.py:87-99 in spirit): sums + count."""
-        return shard.pose_error_scalars(pose, gt)
-
-    # the whole frame as one CUDA graph (falls back to eager launches if capture is not possible)
-    step_fn, graph_note, graph_launches = trk.step, "eager launches", None
+    # the whole frame (+ its eval reduction) as one CUDA graph; --no-graph launches eagerly
+    gs, graph_note, graph_launches = None, "eager launches", None
+    eager_sums = torch.zeros(len(plan), 5 * P + 5, dtype=torch.float32, device=dev)
     if not args.no_graph:
-        try:
-            r0 = resident[0]
-            gs = track.GraphedStep(trk, r0["points"], r0["mean"], r0["pose"])
-            step_fn, graph_note, graph_launches = gs, "one CUDA graph per frame", gs.launches_per_replay
-        except Exception as e:  # noqa: BLE001
-            graph_note = "eager launches (graph capture failed: %s)" % str(e).splitlines()[0][:120]
-            torch.cuda.synchronize(dev)
+        r0 = resident[0]
+        gs = track.GraphedStep(trk, r0["points"], r0["mean"], r0["pose"], gt=pinned[0]["gt"])
+        graph_note, graph_launches = "one CUDA graph per frame (networks, pose fit and the eval reduction)", gs.launches_per_replay
 
-    def step_resident(i):
-        r = resident[i % nb]
-        pose = step_fn(r["points"], r["mean"], r["pose"])
-        ls = shard.all_reduce_scalars(loss_scalars(pose, pinned[i % nb]["gt"]))
-        return pose, ls
+    def run_frame(points, mean, pose, gt):
+        if gs is not None:
+            return gs(points, mean, pose, gt=gt), gs.sums
+        new = trk.step(points, mean, pose)
+        trk.eval_sums(gt, new, out=eager_sums if len(plan) > 1 else eager_sums[0], accumulate=True)
+        return new, eager_sums
+
+    def reset_sums():
+        (gs.sums if gs is not None else eager_sums).zero_()
 
     def barrier():
         if world > 1:
@@ -310,11 +580,11 @@ def main():
 
     # ---- device-resident timing ------------------------------------------------------------
     for i in range(args.warmup):
-        step_resident(i)
+        r = resident[i % nb]
+        run_frame(r["points"], r["mean"], r["pose"], pinned[i % nb]["gt"])
+    reduced = shard.all_reduce_scalars(run_frame(resident[0]["points"], resident[0]["mean"], resident[0]["pose"], pinned[0]["gt"])[1].clone())
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    reset_sums()
     l0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -322,7 +592,10 @@ def main():
     for i in range(args.steps):
         flush.zero_()                      # L2 flush, outside the event pair
         ev[i][0].record(stream)
-        step_resident(i)
+        r = resident[i % nb]
+        _, sums = run_frame(r["points"], r["mean"], r["pose"], pinned[i % nb]["gt"])
+        if i == args.steps - 1:            # end of the batch of frames: ONE all-reduce of the accumulated eval sums
+            reduced = shard.all_reduce_scalars(sums.clone())
         ev[i][1].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -331,22 +604,22 @@ def main():
         launches = graph_launches * args.steps
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(np.sum(step_ms))
+    eval_rows = reduced.detach().cpu()
 
     # ---- end-to-end from host buffers --------------------------------------------------------
     h2d = int(pinned[0]["points"].numel() * 4 + pinned[0]["mean"].numel() * 4 + sum(v.numel() * 4 for v in pinned[0]["pose"].values()))
-    out_host = {k: torch.empty_like(v).pin_memory() for k, v in pinned[0]["pose"].items()}
+    out_host = {k: torch.empty(v.shape, dtype=torch.float32).pin_memory() for k, v in resident[0]["pose"].items()}
     d2h = int(sum(v.numel() * 4 for v in out_host.values()))
 
     def step_e2e(i):
         p = pinned[i % nb]
-        if graph_launches is not None:      # H2D straight into the graph's static input buffers
-            new = step_fn(p["points"], p["mean"], p["pose"])
+        if gs is not None:                  # H2D straight into the graph's static input buffers
+            new, _ = run_frame(p["points"], p["mean"], p["pose"], None)
         else:
             pts = p["points"].to(dev, non_blocking=True)
             mean = p["mean"].to(dev, non_blocking=True)
             pose = {k: v.to(dev, non_blocking=True) for k, v in p["pose"].items()}
-            new = trk.step(pts, mean, pose)
-        shard.all_reduce_scalars(loss_scalars(new, p["gt"]))
+            new, _ = run_frame(pts, mean, pose, p["gt"])
         for k in out_host:
             out_host[k].copy_(new[k], non_blocking=True)
         stream.synchronize()               # the tracker consumes the pose of frame t before frame t+1
@@ -354,11 +627,14 @@ def main():
     for i in range(2):
         step_e2e(i)
     barrier()
+    reset_sums()
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.zero_()
         ev2[i][0].record(stream)
         step_e2e(i)
+        if i == args.steps - 1:
+            shard.all_reduce_scalars((gs.sums if gs is not None else eager_sums).clone()).cpu()     # the reduced metrics reach the host
         ev2[i][1].record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -366,13 +642,15 @@ def main():
 
     # ---- max over ranks -----------------------------------------------------------------------
     tt = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    nfr = torch.tensor([float(Bn)], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(nfr, op=torch.distributed.ReduceOp.SUM)
     total_ms, e2e_ms = float(tt[0]), float(tt[1])
-    frames = B * args.steps * world
+    frames = float(nfr[0]) * args.steps                 # all ranks' trajectories x frames
 
     # ---- profiled pass: per-launch CUDA events (rank 0) -----------------------------------------
-    kernels, roofline = [], None
+    kernels, roofline, extras = [], None, {}
     if rank == 0:
         pk = peaks()
         _lib.PROFILE = []
@@ -415,12 +693,23 @@ def main():
             roofline = {"kernel": top["tag"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm"], "unit": "GB/s",
                         "frac": top["hbm_frac"], "traffic": ncu_traffic(top["tag"]), "peak_source": pk["src"] + " hbm_gbs",
                         "avg_us": top["avg_us"], "share_of_step": top["share_of_step"]}
-        bq = [k for k in kernels if _parse(k["tag"])[0] in ("ball_query_multi", "sa_mlp_max", "sa_mlp_max_pre")]
-        qg_bytes = sum(k["alg_bytes"] * k["launches_per_step"] for k in bq)
-        qg_ms = sum(k["ms_per_step"] for k in bq)
-        query_group = {"what": "ball_query + fused group/MLP/max launches of one step", "alg_bytes_per_step": qg_bytes,
-                       "ms_per_step": qg_ms, "gbs": qg_bytes / (qg_ms * 1e-3) / 1e9 if qg_ms else 0.0,
-                       "frac_of_hbm_peak": (qg_bytes / (qg_ms * 1e-3) / 1e9) / pk["hbm"] if qg_ms else 0.0}
+        mlp_flops = sum(k["alg_flops"] * k["launches_per_step"] for k in kernels)
+        extras["step_tflops"] = mlp_flops / (step_avg_ms * 1e-3) / 1e12
+        if world == 1 and not args.no_extras:
+            del resident
+            torch.cuda.empty_cache()
+            try:
+                extras["query_group"] = query_group_pass(dev, flush, B=64, reps=3)
+            except Exception as e:  # noqa: BLE001
+                extras["query_group"] = {"error": str(e).splitlines()[0][:200]}
+            try:
+                extras["reference_gpu"] = reference_gpu_pass(dev, flush)
+            except Exception as e:  # noqa: BLE001
+                extras["reference_gpu"] = {"error": str(e).splitlines()[0][:200]}
+            try:
+                extras["svd"] = svd_pass(dev, flush)
+            except Exception as e:  # noqa: BLE001
+                extras["svd"] = {"error": str(e).splitlines()[0][:200]}
 
     overflow = mlp.f16_overflowed() if mlp.DEFAULT_IMPL == 2 else None
     if rank != 0:
@@ -430,20 +719,28 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_arm(args.workload, 5, 1, args.cpu_sample)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = cpu_arm_subprocess(args.workload, args.cpu_sample)
 
+    names = [c for c, _ in plan]
+    eval_means = {}
+    if world == 1 or args.workload != "cfg4":
+        for row, c in zip(eval_rows, names):
+            eval_means[c] = frame_ops.eval_means(row, P)
     line = {
         "metric": METRIC, "value": frames / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": dict(config, l2="flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
-                                            mlp_impl={0: "fp32 CUDA cores", 1: "tcgen05 3xTF32", 2: "tcgen05 fp16x3 (fp32 accumulate, overflow-checked)"}[mlp.DEFAULT_IMPL], launch=graph_note, f16_overflow=overflow,
-                                            heads="fused: tcgen05 GEMMs + GroupNorm folded into the operand load (impl 1); torch modules for impl 0", collective="nccl all_reduce of 4 pose-error scalars per step" if world > 1 else "none"),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": dict(config, rank0_plan=["%s x %d" % (c, k) for c, k in plan], frames_per_step_all_ranks=int(frames / args.steps),
+                       l2="flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
+                       mlp_impl={0: "fp32 CUDA cores", 1: "tcgen05 3xTF32", 2: "tcgen05 fp16x3 (fp32 accumulate, overflow-checked)"}[mlp.DEFAULT_IMPL],
+                       launch=graph_note, f16_overflow=overflow,
+                       collective="one nccl all_reduce of the accumulated eval sums [%d x %d floats] after the last timed frame" % (len(plan), 5 * P + 5) if world > 1 else "none"),
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clocks,
-        "roofline": roofline, "query_group": query_group, "kernels": kernels[:12], "cpu_baseline": cpu,
+        "roofline": roofline, "kernels": kernels[:14], "cpu_baseline": cpu, "eval": eval_means,
     }
+    line.update(extras)
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

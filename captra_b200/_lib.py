@@ -30,6 +30,7 @@ SIGNATURES = {
     "three_interpolate_kernel_launcher_fast": [c_int] * 4 + [_P, _P, _P, _P, _P],
     "three_interpolate_grad_kernel_launcher_fast": [c_int] * 4 + [_P, _P, _P, _P, _P],
     "captra_ball_query_multi": [c_int] * 4 + [_P, _P, _P, _P, _P, _P],
+    "captra_ball_query_group": [c_int] * 4 + [c_float, c_int] + [_P] * 6,
     "captra_fps_gather": [c_int] * 3 + [_P, _P, _P, _P, _P],
     "captra_three_nn_interpolate": [c_int] * 4 + [_P] * 7 + [c_int, c_i64, c_int, _P],
     "captra_mlp_pack": [_P, c_int, _P, _P],
@@ -39,12 +40,18 @@ SIGNATURES = {
     "captra_group_norm_affine": [c_int] * 4 + [_P, c_i64, _P, _P, c_float, _P, _P, _P],
     "captra_point_mlp_affine": [c_i64, _P, c_i64, c_int, _P, _P, c_int, _P, _P, _P, c_i64, c_int, c_int, _P],
     "captra_point_mlp_gnstats": [c_i64, _P, c_i64, c_int, _P, _P, c_int, _P, _P, _P, c_i64, c_int, _P, c_int, _P],
+    "captra_group_norm_relu_rows": [c_i64, c_int, c_int, _P, c_i64, _P, _P, _P],
     "captra_group_norm_finalize": [c_int] * 4 + [_P, _P, _P, c_float, _P, _P, _P],
     "captra_debug_tc_timestamps": [_P, c_int],
     "captra_f16_overflow_flag": [c_int],
     "captra_debug_umma_gemm": [c_int, c_int, _P, _P, _P, c_int, _P],
     "captra_procrustes_rot3": [c_i64, _P, _P, _P],
     "captra_procrustes_rot2": [c_i64, _P, _P, _P],
+    "captra_part_fit_track": [c_int] * 3 + [_P] * 5 + [c_int] + [_P] * 6,
+    "captra_canonicalize": [c_int] * 3 + [_P] * 9,
+    "captra_coord_head_post": [c_int] * 4 + [_P, c_i64, _P, c_i64, _P, _P, _P, _P],
+    "captra_rot_head_post": [c_int] * 4 + [_P, c_i64, _P, _P, _P, _P, _P],
+    "captra_track_eval": [c_int] * 5 + [_P] * 14 + [c_int, _P],
     "captra_part_fit_st": [c_int] * 3 + [_P, _P] + [_P] + [c_i64] * 4 + [_P] + [c_i64] * 4 + [_P, _P, c_int, _P, _P, _P, _P, _P],
 }
 OTHER_SYMBOLS = ["captra_last_error", "captra_abi_version", "captra_launch_count", "captra_mlp_pack_bytes"]

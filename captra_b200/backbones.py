@@ -54,22 +54,27 @@ class PointNet2Msg(nn.Module):
             return PackedMLP([w for w, _ in wb], [b for _, b in wb], relu_last=True)
         return self._cache.get(self, build)
 
-    def forward_pm(self, input, geom=None):
-        """input [B,3,N] -> feat [B,N,out_dim] (point-major), fused inference path.  `geom`: an
+    def forward_pm(self, input, geom=None, xyz_pm=None, skip_pm=None):
+        """input [B,3,N] -> feat [B,N,out_dim] (point-major), fused inference path.  The caller may hand over the
+        cloud already point-major (`xyz_pm` [B,N,3], and `skip_pm` [B,N,6] = [xyz, xyz] when use_xyz_feat; both are
+        by-products of captra_canonicalize), in which case `input` is not read.  `geom`: an
         (initially empty) dict that receives every coordinate-only result (FPS picks, ball-query
         index lists, 3-NN indices and weights); passing the same dict to a second backbone that is
         evaluated on the *same* input coordinates reuses them (bit-identical, they depend on xyz only)."""
         g = (lambda k: geom.setdefault(k, {})) if geom is not None else (lambda k: None)
-        l0_xyz = input.transpose(1, 2).contiguous()                       # [B,N,3]
+        l0_xyz = xyz_pm if xyz_pm is not None else input.transpose(1, 2).contiguous()   # [B,N,3]
         l0_feats = l0_xyz if self.use_xyz_feat else None                   # backbones.py:57-60
         l1_xyz, l1_feats = self.sa1.forward_pm(l0_xyz, l0_feats, geom=g("sa1"))
         l2_xyz, l2_feats = self.sa2.forward_pm(l1_xyz, l1_feats, geom=g("sa2"))
         l3_feats = self.sa3.forward_pm(l2_xyz, l2_feats)                   # [B,1024]
-        B = input.shape[0]
-        l3_xyz = torch.zeros(B, 1, 3, device=input.device)
-        l2_feats = self.fp3.forward_pm(l2_xyz, l3_xyz, l2_feats, l3_feats.view(B, 1, -1))
+        B = l0_xyz.shape[0]
+        # fp3 interpolates from the single group-all point: its coordinates (zeros, pointnet_utils.py:176) are never read
+        l2_feats = self.fp3.forward_pm(l2_xyz, None, l2_feats, l3_feats.view(B, 1, -1))
         l1_feats = self.fp2.forward_pm(l1_xyz, l2_xyz, l1_feats, l2_feats, geom=g("fp2"))
-        skip = torch.cat([l0_xyz, l0_xyz], dim=-1) if self.use_xyz_feat else l0_xyz   # backbones.py:67
+        if self.use_xyz_feat:                                                          # backbones.py:67
+            skip = skip_pm if skip_pm is not None else torch.cat([l0_xyz, l0_xyz], dim=-1)
+        else:
+            skip = l0_xyz
         return self.fp1.forward_pm(l0_xyz, l1_xyz, skip, l1_feats, mlp=self._fp1_head(), geom=g("fp1"))
 
     def forward(self, input):  # [B,3,N]

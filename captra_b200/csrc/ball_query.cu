@@ -13,6 +13,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 namespace captra {
 
 constexpr int BQ_THREADS = 256;
@@ -125,11 +127,8 @@ static int launch_bq(int b, int n, int m, const BQParams &prm, const float *new_
     constexpr int CPW = 4;
     auto kern = ball_query_kernel<NR, CPW>;
     const size_t smem = sizeof(float) * 3 * BQ_PLANE;
-    static bool attr_done = false;
-    if (!attr_done) {
-        CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    // per-device attribute, cheap host-side call: set it on every launch (no process-wide flag)
+    CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(m, BQ_WARPS * CPW), b);
     kern<<<grid, BQ_THREADS, smem, stream>>>(n, m, prm, new_xyz, xyz);
     CAPTRA_CHECK_LAUNCH("ball_query");
@@ -277,7 +276,8 @@ template <int QW>
 __global__ void __launch_bounds__(QW * 32)
 bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, const float *__restrict__ new_xyz,
                      const float *__restrict__ xyz, const BQGrid *__restrict__ grids,
-                     const int *__restrict__ cell_start, const float4 *__restrict__ sorted, int *__restrict__ idx) {
+                     const int *__restrict__ cell_start, const float4 *__restrict__ sorted, int *__restrict__ idx,
+                     int gc, const float *__restrict__ gpoints, float *__restrict__ grouped) {
     extern __shared__ unsigned bq_smem[];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ci = blockIdx.x * QW + warp;
@@ -292,6 +292,17 @@ bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, con
     const float *cp = new_xyz + ((size_t)b * m + ci) * 3;
     const float cx = __ldg(cp), cy = __ldg(cp + 1), cz = __ldg(cp + 2);
     int *row = idx + ((size_t)b * m + ci) * nsample;
+    // fused grouping (captra_ball_query_group, few channels): the warp that owns the row also writes
+    // grouped[b, c, ci, :] = points[b, c, row[:]] -- K contiguous floats per channel, no second launch, no idx re-read
+    auto group_row = [&](bool empty) {
+        if (!grouped) return;
+        __syncwarp();
+        for (int l = lane; l < nsample; l += 32) {
+            const int k = empty ? 0 : row[l];          // an empty ball keeps the caller's zeros: index 0
+            for (int c = 0; c < gc; ++c)
+                st_stream(grouped + (((size_t)b * gc + c) * m + ci) * nsample + l, __ldg(gpoints + ((size_t)b * gc + c) * n + k));
+        }
+    };
     const int *cs = cell_start + (size_t)b * (BQG_MAXCELL + 1);
     const float4 *pts = sorted + (size_t)b * n;
     __syncwarp();
@@ -369,9 +380,10 @@ bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, con
             }
         }
         for (int l = have + lane; l < nsample; l += 32) row[l] = first;
+        group_row(have == 0);
         return;
     }
-    if (cnt == 0) return;                      // empty ball: the caller's zeros stay
+    if (cnt == 0) { group_row(true); return; }   // empty ball: the caller's zeros stay
     __syncwarp();
     // ---- read the bitmap back in index order: per-lane popcount, warp prefix, ordered emission
     int c = 0;
@@ -394,53 +406,64 @@ bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, con
     __syncwarp();
     const int keep = min(cnt, nsample), first = stage[0];
     for (int l = lane; l < nsample; l += 32) row[l] = l < keep ? stage[l] : first;
+    group_row(false);
 }
 
 static int launch_bq_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
-                          int *idx, cudaStream_t stream) {
+                          int *idx, cudaStream_t stream, int gc = 0, const float *gpoints = nullptr, float *grouped = nullptr) {
     // stream-ordered scratch: grid descriptors, cell starts, binned points
     const size_t sz_g = sizeof(BQGrid) * (size_t)b;
     const size_t sz_c = sizeof(int) * (size_t)b * (BQG_MAXCELL + 1);
     const size_t sz_s = sizeof(float4) * (size_t)b * n;
     const size_t off_c = (sz_g + 255) & ~(size_t)255, off_s = (off_c + sz_c + 255) & ~(size_t)255;
-    uint8_t *ws = nullptr;
-    static bool pool_done = false;
-    if (!pool_done) {
-        // keep freed scratch in the stream-ordered pool across synchronisation points (default threshold 0
-        // hands it back to the driver at every sync, and the next frame pays a fresh allocation)
-        int dev = 0;
-        cudaMemPool_t pool;
-        CAPTRA_CUDA(cudaGetDevice(&dev));
-        CAPTRA_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-        unsigned long long thr = ~0ull;
-        CAPTRA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        pool_done = true;
+    // Scratch comes from a stream-ordered pool OWNED by this library (one per device, created on first use, release
+    // threshold raised so freed scratch is reused by the next frame instead of going back to the driver at every
+    // synchronisation).  The process's default pool -- torch's, or anybody else's -- is not touched.
+    static std::mutex pool_mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    CAPTRA_CUDA(cudaGetDevice(&dev));
+    CAPTRA_REQUIRE(dev >= 0 && dev < 64, "ball_query: device index %d out of range", dev);
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> lock(pool_mu);
+        if (!pools[dev]) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            CAPTRA_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+            unsigned long long thr = ~0ull;
+            CAPTRA_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &thr));
+        }
+        pool = pools[dev];
     }
-    CAPTRA_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), off_s + sz_s, stream));
+    uint8_t *ws = nullptr;
+    CAPTRA_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), off_s + sz_s, pool, stream));
+    struct Guard {              // every early return below hands the scratch back
+        uint8_t *p; cudaStream_t s;
+        ~Guard() { if (p) cudaFreeAsync(p, s); }
+    } guard{ws, stream};
     BQGrid *grids = reinterpret_cast<BQGrid *>(ws);
     int *cell_start = reinterpret_cast<int *>(ws + off_c);
     float4 *sorted = reinterpret_cast<float4 *>(ws + off_s);
     const size_t smem = sizeof(int) * (BQG_MAXCELL + 1);
-    static bool attr_done = false;
-    if (!attr_done) {
-        CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_query_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10));
-        CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_query_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQG_MAX_SMEM));
-        attr_done = true;
-    }
+    CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_query_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10));
+    CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_query_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQG_MAX_SMEM));
     bq_grid_build_kernel<<<b, 1024, smem, stream>>>(n, radius, xyz, grids, cell_start, sorted);
     CAPTRA_CHECK_LAUNCH("ball_query(grid build)");
     const int wpl_log2 = bq_grid_wpl_log2(n);
     const size_t per_warp = sizeof(int) * (32 * ((1 << wpl_log2) | 1) + (size_t)nsample);
     if (4 * per_warp <= (64u << 10))
         bq_grid_query_kernel<4><<<dim3(ceil_div(m, 4), b), 128, 4 * per_warp, stream>>>(
-            n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids, cell_start, sorted, idx);
+            n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids, cell_start, sorted, idx, gc, gpoints, grouped);
     else
         bq_grid_query_kernel<1><<<dim3(m, b), 32, per_warp, stream>>>(
-            n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids, cell_start, sorted, idx);
+            n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids, cell_start, sorted, idx, gc, gpoints, grouped);
     CAPTRA_CHECK_LAUNCH("ball_query(grid query)");
-    CAPTRA_CUDA(cudaFreeAsync(ws, stream));
-    return CAPTRA_OK;
+    return CAPTRA_OK;           // ~Guard frees the scratch (stream-ordered, after the query kernel)
 }
 
 }  // namespace captra
@@ -480,6 +503,27 @@ extern "C" int captra_ball_query_multi(int b, int n, int m, int nradii, const fl
         case 3: return launch_bq<3>(b, n, m, prm, new_xyz, xyz, s);
         default: return launch_bq<4>(b, n, m, prm, new_xyz, xyz, s);
     }
+}
+
+// in group_gather.cu
+extern "C" int group_points_kernel_launcher_fast(int b, int c, int n, int npoints, int nsample, const float *points,
+                                                 const int *idx, float *out, captra_stream_t stream);
+
+extern "C" int captra_ball_query_group(int b, int n, int m, int c, float radius, int nsample, const float *new_xyz,
+                                       const float *xyz, const float *points, int *idx, float *grouped,
+                                       captra_stream_t stream) {
+    CAPTRA_REQUIRE(b >= 0 && n >= 0 && m >= 0 && c >= 0 && nsample >= 0, "ball_query_group: negative size");
+    CAPTRA_REQUIRE(b <= 65535, "ball_query_group: batch %d exceeds grid.y limit", b);
+    if (b == 0 || m == 0 || n == 0 || nsample == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(new_xyz && xyz && idx && (c == 0 || (points && grouped)), "ball_query_group: null pointer");
+    static const int grid_min_n = [] { const char *e = getenv("CAPTRA_BQ_GRID_MIN_N"); return e ? atoi(e) : 2048; }();
+    // few channels (SA level 1 groups the coordinates themselves): the query warp writes the grouped rows itself
+    if (c >= 1 && c <= 8 && n >= grid_min_n && radius > 0.f && isfinite(radius) && bq_grid_fits(n, nsample))
+        return launch_bq_grid(b, n, m, radius, nsample, new_xyz, xyz, idx, as_stream(stream), c, points, grouped);
+    // wide rows: the query, then the shared-memory-staged gather (the HBM-bound part, group_gather.cu)
+    int rc = captra_ball_query_multi(b, n, m, 1, &radius, &nsample, new_xyz, xyz, &idx, stream);
+    if (rc != CAPTRA_OK || c == 0) return rc;
+    return group_points_kernel_launcher_fast(b, c, n, m, nsample, points, idx, grouped, stream);
 }
 
 extern "C" int ball_query_kernel_launcher_fast(int b, int n, int m, float radius, int nsample,

@@ -41,7 +41,7 @@ fps_reg_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *cloud = dataset + (size_t)b * n * 3;
-    float *tmp = temp + (size_t)b * n;
+    float *tmp = temp ? temp + (size_t)b * n : nullptr;   // null: running distances start at 1e10 and are not returned
     int *out = idxs + (size_t)b * m;
     float *oxyz = new_xyz ? new_xyz + (size_t)b * m * 3 : nullptr;
     float *sx = smem, *sy = smem + n, *sz = smem + 2 * n;
@@ -60,7 +60,7 @@ fps_reg_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
         const int k = tid + j * NT;
         const bool ok = k < n;
         x[j] = ok ? sx[k] : 0.f; y[j] = ok ? sy[k] : 0.f; z[j] = ok ? sz[k] : 0.f;
-        t[j] = ok ? tmp[k] : -INFINITY;  // never wins, never ties a real point
+        t[j] = ok ? (tmp ? tmp[k] : 1e10f) : -INFINITY;  // -inf never wins, never ties a real point
     }
 
     int old = 0;
@@ -106,10 +106,12 @@ fps_reg_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
     }
 
     // the reference leaves its running min-distances in the caller's scratch
+    if (tmp) {
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-        const int k = tid + j * NT;
-        if (k < n) tmp[k] = t[j];
+        for (int j = 0; j < PPT; ++j) {
+            const int k = tid + j * NT;
+            if (k < n) tmp[k] = t[j];
+        }
     }
 }
 
@@ -185,7 +187,8 @@ extern "C" int captra_fps_gather(int b, int n, int m, const float *dataset, floa
     if (b == 0 || m <= 0) return CAPTRA_OK;  // sampling_gpu.cu:101 `if (m <= 0) return`
     CAPTRA_REQUIRE(n >= 1, "fps: empty cloud with m > 0");
     CAPTRA_REQUIRE(n < (1 << 22), "fps: n=%d exceeds the 2^22 key width", n);
-    CAPTRA_REQUIRE(dataset && temp && idxs, "fps: null pointer");
+    CAPTRA_REQUIRE(dataset && idxs, "fps: null pointer");
+    CAPTRA_REQUIRE(temp || n <= 8192, "fps: clouds above 8192 points keep their running distances in `temp` (must not be NULL)");
     // block = min(1024, 2^floor(log2 n)) (cuda_utils.h:10-14); exact integer log2 here -- the
     // reference's log()/log() quotient evaluates to the same integer for every n < 2^22
     // (checked exhaustively in tests/test_oracle.py).

@@ -213,9 +213,33 @@ __global__ void __launch_bounds__(RH_THREADS) rot_head_post_kernel(RotHeadArgs a
         }
 }
 
+// ---- GroupNorm + ReLU applied in place (cloud sizes that are not a multiple of the 128-row tile) ----------------
+__global__ void __launch_bounds__(256) gn_relu_rows_kernel(int64_t rows, int c, int rows_per_cloud, float *__restrict__ y, int64_t ld,
+                                                           const float *__restrict__ scale, const float *__restrict__ shift) {
+    const int64_t total = rows * c;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / c;
+        const int ch = (int)(e - r * c);
+        const int64_t cloud = r / rows_per_cloud;
+        float *p = y + r * ld + ch;
+        *p = fmaxf(fmaf(*p, __ldg(scale + cloud * c + ch), __ldg(shift + cloud * c + ch)), 0.f);
+    }
+}
+
 }  // namespace captra
 
 using namespace captra;
+
+extern "C" int captra_group_norm_relu_rows(int64_t rows, int c, int rows_per_cloud, float *y, int64_t ldy, const float *scale,
+                                           const float *shift, captra_stream_t stream) {
+    CAPTRA_REQUIRE(rows >= 0 && c >= 1 && rows_per_cloud >= 1 && ldy >= c, "group_norm_relu_rows: bad sizes");
+    if (rows == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(y && scale && shift, "group_norm_relu_rows: null pointer");
+    const int64_t blocks = ceil_div<int64_t>(rows * c, 256);
+    gn_relu_rows_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, as_stream(stream)>>>(rows, c, rows_per_cloud, y, ldy, scale, shift);
+    CAPTRA_CHECK_LAUNCH("group_norm_relu_rows");
+    return CAPTRA_OK;
+}
 
 extern "C" int captra_canonicalize(int b, int p, int n, const float *points, const float *points_mean,
                                    const float *rotation, const float *translation, const float *scale,

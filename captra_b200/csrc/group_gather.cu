@@ -143,11 +143,8 @@ static int launch_gather(const char *name, int b, int c, int n, int64_t L, const
         splits = (int)ceil_div<int64_t>(L, chunk);
         if (nblk <= 65535) {
             auto kern = vec ? gather_rows_smem_kernel<true> : gather_rows_smem_kernel<false>;
-            static size_t attr_smem[2] = {0, 0};
-            if (smem > attr_smem[vec]) {
-                CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-                attr_smem[vec] = kSmemMax;
-            }
+            // per-device attribute: set on every launch (no process-wide flag)
+            CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
             kern<<<dim3(splits, nblk, b), GS_THREADS, smem, stream>>>(c, n, L, cb, chunk, points, idx, out);
             CAPTRA_CHECK_LAUNCH(name);
             return CAPTRA_OK;

@@ -196,6 +196,11 @@ struct PFArgs {
     const float *rotation;     // [B,P,3,3] or null
     const float *given_scale;  // [B,P] or null
     float *scale, *translation; uint8_t *valid; float *rot_out;
+    // tracker extras (captra_part_fit_track): target = target + target_add[b] on load (the cam + points_mean of
+    // networks.py:220-221), and the validity blend with the previous pose (networks.py:230-232)
+    const float *target_add;   // [B,3] or null
+    const float *prev_scale;   // [B,P] or null
+    const float *prev_translation;  // [B,P,3] or null
 };
 
 __global__ void __launch_bounds__(PF_THREADS) part_fit_kernel(PFArgs a) {
@@ -205,6 +210,11 @@ __global__ void __launch_bounds__(PF_THREADS) part_fit_kernel(PFArgs a) {
     const float *tgt = a.target + b * a.tsb + part * a.tsp;
     const int64_t *lab = a.labels ? a.labels + (size_t)b * a.n : nullptr;
     const float *msk = a.mask ? a.mask + (size_t)bp * a.n : nullptr;
+    const bool add = a.target_add != nullptr;
+    const float ta0 = add ? a.target_add[b * 3 + 0] : 0.f, ta1 = add ? a.target_add[b * 3 + 1] : 0.f,
+                ta2 = add ? a.target_add[b * 3 + 2] : 0.f;
+    // x + 0.f is exact, so one code path serves both entry points
+    auto T = [&](int i, int c, float off) { return __fadd_rn(__ldg(tgt + i * a.tsn + c * a.tsc), off); };
 
     // pass 1: count and centroids (procrustes.py:137-138)
     float c = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f;
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(PF_THREADS) part_fit_kernel(PFArgs a) {
         if (in) {
             c += 1.f;
             s0 += __ldg(src + i * a.ssn); s1 += __ldg(src + i * a.ssn + a.ssc); s2 += __ldg(src + i * a.ssn + 2 * a.ssc);
-            t0 += __ldg(tgt + i * a.tsn); t1 += __ldg(tgt + i * a.tsn + a.tsc); t2 += __ldg(tgt + i * a.tsn + 2 * a.tsc);
+            t0 += T(i, 0, ta0); t1 += T(i, 1, ta1); t2 += T(i, 2, ta2);
         }
     }
     double v1[7] = {c, s0, s1, s2, t0, t1, t2};
@@ -230,8 +240,7 @@ __global__ void __launch_bounds__(PF_THREADS) part_fit_kernel(PFArgs a) {
         if (in) {
             const float x0 = __ldg(src + i * a.ssn) - sc0, x1 = __ldg(src + i * a.ssn + a.ssc) - sc1,
                         x2 = __ldg(src + i * a.ssn + 2 * a.ssc) - sc2;
-            const float y0 = __ldg(tgt + i * a.tsn) - tc0, y1 = __ldg(tgt + i * a.tsn + a.tsc) - tc1,
-                        y2 = __ldg(tgt + i * a.tsn + 2 * a.tsc) - tc2;
+            const float y0 = T(i, 0, ta0) - tc0, y1 = T(i, 1, ta1) - tc1, y2 = T(i, 2, ta2) - tc2;
             h[0] += y0 * x0; h[1] += y0 * x1; h[2] += y0 * x2;
             h[3] += y1 * x0; h[4] += y1 * x1; h[5] += y1 * x2;
             h[6] += y2 * x0; h[7] += y2 * x1; h[8] += y2 * x2;
@@ -284,8 +293,6 @@ __global__ void __launch_bounds__(PF_THREADS) part_fit_kernel(PFArgs a) {
 
     const float fs = (float)scale;
     const float ft[3] = {(float)tr[0], (float)tr[1], (float)tr[2]};
-    a.scale[bp] = fs;
-    for (int i = 0; i < 3; ++i) a.translation[(size_t)bp * 3 + i] = ft[i];
     // pose_fit.py:26-35,46 -- the *returned* rotation is the input one, so its finiteness is
     // what filter_model_valid sees when a rotation is given
     float rsum = 0.f;
@@ -296,6 +303,16 @@ __global__ void __launch_bounds__(PF_THREADS) part_fit_kernel(PFArgs a) {
             for (int j = 0; j < 3; ++j) rsum += (float)R[i][j];
     const bool ok = (cnt > 3.0) && isfinite(fs) && isfinite(ft[0] + ft[1] + ft[2]) && isfinite(rsum);
     a.valid[bp] = ok ? 1 : 0;
+    if (a.prev_scale) {
+        // networks.py:230-232: valid * new + (1 - valid) * previous, in fp32 exactly as written there (a NaN fit
+        // stays NaN: 0 * NaN)
+        const float v = ok ? 1.f : 0.f;
+        a.scale[bp] = v * fs + (1.f - v) * a.prev_scale[bp];
+        for (int i = 0; i < 3; ++i) a.translation[(size_t)bp * 3 + i] = v * ft[i] + (1.f - v) * a.prev_translation[(size_t)bp * 3 + i];
+    } else {
+        a.scale[bp] = fs;
+        for (int i = 0; i < 3; ++i) a.translation[(size_t)bp * 3 + i] = ft[i];
+    }
     if (a.rot_out)
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) a.rot_out[(size_t)bp * 9 + i * 3 + j] = (float)R[i][j];
@@ -340,7 +357,30 @@ extern "C" int captra_part_fit_st(int b, int p, int n, const int64_t *labels, co
     a.target = target; a.tsb = tsb; a.tsp = tsp; a.tsn = tsn; a.tsc = tsc;
     a.rotation = rotation; a.given_scale = given_scale;
     a.scale = scale; a.translation = translation; a.valid = valid; a.rot_out = rot_out;
+    a.target_add = nullptr; a.prev_scale = nullptr; a.prev_translation = nullptr;
     part_fit_kernel<<<b * p, PF_THREADS, 0, as_stream(stream)>>>(a);
     CAPTRA_CHECK_LAUNCH("part_fit_st");
+    return CAPTRA_OK;
+}
+
+extern "C" int captra_part_fit_track(int b, int p, int n, const int64_t *labels, const float *nocs, const float *points,
+                                     const float *points_mean, const float *rotation, int sym, const float *prev_scale,
+                                     const float *prev_translation, float *scale, float *translation, uint8_t *valid,
+                                     captra_stream_t stream) {
+    CAPTRA_REQUIRE(b >= 0 && p >= 0 && n >= 0, "part_fit_track: negative size");
+    if (b == 0 || p == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(labels && nocs && points && points_mean && rotation && prev_scale && prev_translation && scale &&
+                       translation && valid, "part_fit_track: null pointer");
+    PFArgs a;
+    a.p = p; a.n = n; a.sym = sym; a.labels = labels; a.mask = nullptr;
+    // source = pred_npcs [B,P,3,N] read as [B,P,N,3] (networks.py:227 transposes the view); target = the cloud
+    // [B,3,N] + points_mean, shared by all parts (the `repeat` of networks.py:221 is a zero part stride)
+    a.source = nocs; a.ssb = (int64_t)p * 3 * n; a.ssp = (int64_t)3 * n; a.ssn = 1; a.ssc = n;
+    a.target = points; a.tsb = (int64_t)3 * n; a.tsp = 0; a.tsn = 1; a.tsc = n;
+    a.rotation = rotation; a.given_scale = nullptr;
+    a.scale = scale; a.translation = translation; a.valid = valid; a.rot_out = nullptr;
+    a.target_add = points_mean; a.prev_scale = prev_scale; a.prev_translation = prev_translation;
+    part_fit_kernel<<<b * p, PF_THREADS, 0, as_stream(stream)>>>(a);
+    CAPTRA_CHECK_LAUNCH("part_fit_track");
     return CAPTRA_OK;
 }

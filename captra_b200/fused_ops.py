@@ -14,9 +14,9 @@ def fps_gather(xyz, npoint):
     B, N, _ = xyz.shape
     idx = torch.empty(B, npoint, dtype=_i32, device=xyz.device)
     new_xyz = torch.empty(B, npoint, 3, dtype=_f32, device=xyz.device)
-    temp = torch.full((B, N), 1e10, dtype=_f32, device=xyz.device)
+    temp = torch.full((B, N), 1e10, dtype=_f32, device=xyz.device) if N > 8192 else None   # registers below that
     _lib.call("fps_gather[B=%d,N=%d,M=%d]" % (B, N, npoint), _lib.load().captra_fps_gather, B, N, npoint,
-              _lib.ptr(xyz, _f32, "xyz"), temp.data_ptr(), idx.data_ptr(), new_xyz.data_ptr(),
+              _lib.ptr(xyz, _f32, "xyz"), temp.data_ptr() if temp is not None else None, idx.data_ptr(), new_xyz.data_ptr(),
               _lib.stream_ptr(xyz.device), device=xyz.device)
     return idx, new_xyz
 
@@ -26,7 +26,12 @@ def ball_query_multi(radii, nsamples, xyz, new_xyz):
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     nr = len(radii)
-    outs = [torch.zeros(B, S, k, dtype=_i32, device=xyz.device) for k in nsamples]
+    # one zeroed allocation for all radii (empty balls keep their zeros, pointnet2_utils.py:261): one fill, not nr
+    flat = torch.zeros(B * S * sum(int(k) for k in nsamples), dtype=_i32, device=xyz.device)
+    outs, off = [], 0
+    for k in nsamples:
+        outs.append(flat[off:off + B * S * int(k)].view(B, S, int(k)))
+        off += B * S * int(k)
     ra = (ctypes.c_float * nr)(*[float(r) for r in radii])
     ka = (ctypes.c_int * nr)(*[int(k) for k in nsamples])
     pa = (ctypes.c_void_p * nr)(*[o.data_ptr() for o in outs])
@@ -34,6 +39,19 @@ def ball_query_multi(radii, nsamples, xyz, new_xyz):
               _lib.load().captra_ball_query_multi, B, N, S, nr, ra, ka, _lib.ptr(new_xyz, _f32, "new_xyz"),
               _lib.ptr(xyz, _f32, "xyz"), pa, _lib.stream_ptr(xyz.device), device=xyz.device)
     return outs
+
+
+def ball_query_group(radius, nsample, xyz, new_xyz, features):
+    """QueryAndGroup without the concat (pointnet2_utils.py:290-296): xyz [B,N,3], new_xyz [B,M,3], features [B,C,N]
+    -> (idx [B,M,K] int32, grouped [B,C,M,K]); one C-ABI call (captra_ball_query_group)."""
+    B, N, _ = xyz.shape
+    M, C = new_xyz.shape[1], features.shape[1]
+    idx = torch.zeros(B, M, nsample, dtype=_i32, device=xyz.device)
+    out = torch.empty(B, C, M, nsample, dtype=_f32, device=xyz.device)
+    _lib.call("ball_query_group[B=%d,N=%d,M=%d,K=%d,C=%d]" % (B, N, M, nsample, C), _lib.load().captra_ball_query_group,
+              B, N, M, C, float(radius), int(nsample), _lib.ptr(new_xyz, _f32, "new_xyz"), _lib.ptr(xyz, _f32, "xyz"),
+              _lib.ptr(features, _f32, "features"), idx.data_ptr(), out.data_ptr(), _lib.stream_ptr(xyz.device), device=xyz.device)
+    return idx, out
 
 
 def three_nn_interpolate_pm(unknown, known, feats_pm, out=None, col_off=0, nn=None, return_nn=False):

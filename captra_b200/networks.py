@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib, frame_ops
 from . import mlp as _mlp
 from .backbones import PointNet2Msg
 from .mlp import PackedMLP, fold_conv_bn, group_norm_affine, group_norm_finalize
@@ -120,10 +121,22 @@ class MLPConv1d(nn.Module):
         gns = [m for m in self.model if isinstance(m, nn.GroupNorm)]
         if not hasattr(self, "_cache"):
             self._cache = _FusedCache()
+        # GroupNorm-on-load exists on the tensor-core kernels only: CAPTRA_MLP_IMPL=0 (exact-fp32 SA / FP MLPs, a
+        # testing knob) keeps the heads on the default tcgen05 variant
+        himpl = _mlp.DEFAULT_IMPL if _mlp.DEFAULT_IMPL in (1, 2) else 2
         packs = self._cache.get(self, lambda: [PackedMLP([c.weight.detach().reshape(c.out_channels, c.in_channels)],
-                                                         [c.bias.detach()], relu_last=False, impl=_mlp.DEFAULT_IMPL) for c in convs])
+                                                         [c.bias.detach()], relu_last=False, impl=himpl) for c in convs])
         x = feat_pm.reshape(B * N, C)
-        if N % 128 != 0 or os.environ.get("CAPTRA_GN_FUSED", "1") == "0":     # unfused statistics pass (odd cloud sizes; A/B knob)
+        if N % 128 != 0:      # a 128-row tile would straddle clouds: statistics pass + in-place GroupNorm/ReLU + plain rows
+            y = packs[0].rows(x)
+            for i in range(1, len(convs)):
+                scale, shift = group_norm_affine(y, B, N, gns[i - 1])
+                _lib.call("group_norm_relu_rows[R=%d,C=%d]" % (y.shape[0], y.shape[1]), _lib.load().captra_group_norm_relu_rows,
+                          y.shape[0], y.shape[1], N, y.data_ptr(), y.stride(0), scale.data_ptr(), shift.data_ptr(),
+                          _lib.stream_ptr(y.device), device=y.device)
+                y = packs[i].rows(y)
+            return y.view(B, N, -1)
+        if os.environ.get("CAPTRA_GN_FUSED", "1") == "0":     # unfused statistics pass (A/B knob)
             y = packs[0].rows(x)
             for i in range(1, len(convs)):
                 scale, shift = group_norm_affine(y, B, N, gns[i - 1])
@@ -192,14 +205,21 @@ class CoordNet(nn.Module):
 
     def forward(self, input, test=False):
         assert 'gt_part' not in input, "training-time pose branch (networks.py:54-108) is not mirrored"
-        cam = canonicalize(input['points'], input['points_mean'], input['canon_pose'])
-        if not _needs_autograd(self, cam):
-            feat = self.backbone.forward_pm(cam, geom=input.get('geom'))   # [B,N,C] point-major
+        if not _needs_autograd(self, input['points']):
+            pose = input['canon_pose']
+            geom = input.get('geom')
+            xyz_pm, cam, dup = frame_ops.canonicalize(input['points'], input['points_mean'], pose['rotation'],
+                                                      pose['translation'], pose['scale'], want_cm=True, want_dup=True)
+            if geom is not None:
+                geom['xyz_pm'] = xyz_pm      # a rigid object's RotationNet sees the very same canonical cloud
+            feat = self.backbone.forward_pm(None, geom=geom, xyz_pm=xyz_pm, skip_pm=dup)   # [B,N,C] point-major
             B, N, C = feat.shape
             seg_mlp, nocs_mlp = self._packed_heads()
-            seg = F.softmax(seg_mlp.rows(feat.reshape(B * N, C)).view(B, N, -1), dim=-1).transpose(1, 2)
-            nocs = (torch.sigmoid(nocs_mlp.rows(feat.reshape(B * N, C))) - 0.5).view(B, N, -1).transpose(1, 2)
-            return {'seg': seg, 'nocs': nocs, 'points': cam}
+            x = feat.reshape(B * N, C)
+            labels, nocs, seg = frame_ops.coord_head_post(seg_mlp.rows(x), nocs_mlp.rows(x), B, N)
+            # 'labels' (= torch.max(seg, dim=-2)[1], model.py:458) is an extra key for the tracker
+            return {'seg': seg, 'nocs': nocs, 'points': cam, 'labels': labels}
+        cam = canonicalize(input['points'], input['points_mean'], input['canon_pose'])
         feat = self.backbone(cam)
         seg = F.softmax(self.seg_head(feat), dim=1)
         nocs = self.nocs_head(feat) - 0.5
@@ -216,33 +236,30 @@ class RotationRegressionBackbone(nn.Module):
         self.sym = cfg['obj_sym']
         self.pose_pred = RotationRegressor(cfg['network']['backbone_out_dim'], self.num_parts, symmetric=self.sym)
 
-    def forward_diag(self, cam, labels, batch_size, geom=None):
-        """cam [B*P,3,N] (copy p canonicalised by part p), labels [B,N] -> rtvec [B,P,D]: head p on
-        copy p, masked mean over part p's points (networks.py:127-139 restricted to the diagonal
-        that networks.py:200-203 keeps)."""
+    def forward_rotation(self, xyz_pm, labels, rot_prev, batch_size, geom=None, want_rtvec=False):
+        """Fused inference path: xyz_pm [B*P,N,3] (copy p canonicalised by part p), labels [B,N], rot_prev [B,P,3,3]
+        -> rotation [B,P,3,3] = rot_prev . dR: encoder, head p on copy p (networks.py:200-203 keeps that diagonal only),
+        then ONE launch for per-point 6-D / 3-D -> matrix, masked mean, default, Gram-Schmidt and composition."""
         P = self.num_parts
-        fused = _mlp.DEFAULT_IMPL in (1, 2) and not _needs_autograd(self, cam)
-        if fused:
-            feat_pm = self.encoder.forward_pm(cam, geom=geom)      # [B*P, N, C] point-major
-            feat_pm = feat_pm.reshape(batch_size, P, feat_pm.shape[1], feat_pm.shape[2])
-        else:
-            feat = self.encoder(cam)                               # [B*P, C, N]
-            feat = feat.reshape(batch_size, P, feat.shape[1], feat.shape[2])
+        feat_pm = self.encoder.forward_pm(None, geom=geom, xyz_pm=xyz_pm)      # [B*P, N, C]
+        feat_pm = feat_pm.reshape(batch_size, P, feat_pm.shape[1], feat_pm.shape[2])
+        raws = [self.pose_pred.rtvec_head[p].forward_pm(feat_pm[:, p] if P == 1 else feat_pm[:, p].contiguous()) for p in range(P)]
+        return frame_ops.rot_head_post(raws, labels, rot_prev, self.sym, want_rtvec=want_rtvec)
+
+    def forward_diag(self, cam, labels, batch_size):
+        """Autograd / training-mode path in torch ops, as the reference composes it: cam [B*P,3,N] (copy p
+        canonicalised by part p), labels [B,N] -> rtvec [B,P,D]: head p on copy p, masked mean over part p's points
+        (networks.py:127-139 restricted to the diagonal that networks.py:200-203 keeps)."""
+        P = self.num_parts
+        feat = self.encoder(cam)                               # [B*P, C, N]
+        feat = feat.reshape(batch_size, P, feat.shape[1], feat.shape[2])
         out = []
         for p in range(P):
-            if fused:
-                raw = self.pose_pred.rtvec_head[p].forward_pm(feat_pm[:, p].contiguous()).transpose(1, 2)
-            else:
-                raw = self.pose_pred.rtvec_head[p](feat[:, p])
-            raw = self.pose_pred.post(raw)                                          # [B, D, N]
+            raw = self.pose_pred.post(self.pose_pred.rtvec_head[p](feat[:, p]))    # [B, D, N]
             mask = (labels == p).float().unsqueeze(1)                               # [B, 1, N]
             cnt = mask.sum(-1)
             mean = (raw * mask).sum(-1) / torch.clamp_min(cnt, 1.0)
-            if self.sym:                   # defaults built on the device (CUDA-graph capturable)
-                default = torch.zeros(3, device=raw.device)
-                default[1:2] = 1.0         # slice, not an int index: the latter copies a CPU scalar (not capturable)
-            else:
-                default = torch.eye(3, device=raw.device).reshape(-1)
+            default = torch.tensor((0., 1., 0.) if self.sym else (1., 0., 0., 0., 1., 0., 0., 0., 1.), device=raw.device)
             valid = (cnt > 0).float()
             out.append(valid * mean + (1.0 - valid) * default.reshape(1, -1))
         return torch.stack(out, dim=1)
@@ -273,12 +290,22 @@ class PartCanonNet(nn.Module):
         B = len(cam)
         points_mean = input['points_mean']          # [B,3,1]
         labels = input['pred_labels']               # [B,N]
+        if not _needs_autograd(self, cam):
+            shared = input.get('geom') if P == 1 and 'canon_pose' not in input else None
+            if shared is not None and 'xyz_pm' in shared:
+                xyz_pm = shared['xyz_pm']            # rigid object: CoordNet canonicalised by the same pose
+            else:
+                xyz_pm = frame_ops.canonicalize(cam, points_mean, canon_pose['rotation'], canon_pose['translation'],
+                                                canon_pose['scale'], parts=P)[0]
+            rotation = self.regress_net.forward_rotation(xyz_pm, labels, part_pose['rotation'], B, geom=shared)
+            pred_npcs = input['pred_nocs'].reshape(B, P, 3, -1)
+            scale, translation, _ = frame_ops.part_fit_track(labels, pred_npcs.contiguous(), cam, points_mean, rotation, self.sym,
+                                                             part_pose['scale'], part_pose['translation'])
+            return {'part': {'rotation': rotation, 'scale': scale, 'translation': translation}}
         cam_rep = cam.unsqueeze(1).expand(-1, P, -1, -1).reshape((-1,) + cam.shape[-2:])
         mean_rep = points_mean.unsqueeze(1).expand(-1, P, -1, -1).reshape((-1,) + points_mean.shape[-2:])
         cam_rep = canonicalize(cam_rep, mean_rep, canon_pose)
-        # a rigid object (P == 1) is canonicalised by the same pose in both networks: share the geometry
-        geom = input.get('geom') if P == 1 and 'canon_pose' not in input else None
-        rtvec = self.regress_net.forward_diag(cam_rep, labels, B, geom=geom)    # [B,P,D]
+        rtvec = self.regress_net.forward_diag(cam_rep, labels, B)               # [B,P,D]
         delta_rot = convert_pred_rtvec_to_matrix(rtvec, self.sym)                # [B,P,3,3]
         rotation = torch.matmul(part_pose['rotation'], delta_rot)                # part_dof_utils.py:124-128
         pred_npcs = input['pred_nocs'].reshape(B, P, 3, -1)

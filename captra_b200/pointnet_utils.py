@@ -283,7 +283,7 @@ class PointNetFeaturePropagation(nn.Module):
         points2 [B,S,D2] -> [B,N,cout].  `mlp` lets the caller append layers (backbones.py:68);
         `geom` caches the 3-NN indices/weights for a second network on the same coordinates."""
         B, N, _ = xyz1_pm.shape
-        S = xyz2_pm.shape[1]
+        S = points2_pm.shape[1]
         mlp = mlp or self._packed()
         segA = points1_pm.reshape(B * N, -1) if points1_pm is not None and points1_pm.shape[-1] > 0 else None
         if S == 1:  # pointnet_utils.py:281-282: repeat the single coarse point

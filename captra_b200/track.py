@@ -165,12 +165,69 @@ class Tracker(torch.nn.Module):
         pred = self.npcs_net({"points": points, "points_mean": points_mean, "canon_pose": canon, "geom": geom})
         B = points.shape[0]
         pred_npcs = pred["nocs"].reshape(B, self.num_parts, 3, -1)
-        pred_labels = torch.max(pred["seg"], dim=-2)[1]
+        pred_labels = pred["labels"] if "labels" in pred else torch.max(pred["seg"], dim=-2)[1]
         out = self.net({"points": points, "points_mean": points_mean, "state": {"part": last_pose},
                         "pred_labels": pred_labels, "pred_nocs": pred_npcs, "geom": geom}, test_mode=True)
         if want_pred:
             return out["part"], {"seg": pred["seg"], "nocs": pred["nocs"], "labels": pred_labels, "points": pred["points"]}
         return out["part"]
+
+    def eval_sums(self, gt, pose, **kw):
+        """Per-frame pose-error sums of model.py:523-526 (eval_part_full, yaxis_only = sym) on the device:
+        [1, 5P + 5], additive over trajectories and ranks (frame_ops.track_eval / eval_means)."""
+        from . import frame_ops
+        return frame_ops.track_eval(gt, pose, self.cfg["obj_sym"], **kw).view(1, -1)
+
+
+class MixedTracker(torch.nn.Module):
+    """BASELINE cfg4: one batch holding trajectories of several NOCS categories, each category with its own pair of
+    networks (the reference tracks one category per checkpoint: scripts/track/nocs/1_bottle.sh ... 6_mug.sh,
+    --obj_category=k).  The batch is kept GROUPED BY CATEGORY (group_by_category gives the permutation), so each
+    category's clouds are one contiguous slice: no gather / scatter, every group runs its own launch set on its own
+    weights, and the result is identical -- bit for bit -- to running each category's Tracker alone on its slice."""
+
+    def __init__(self, categories, device="cuda:0", seed=0):
+        """categories: the category NAME of every cloud of the (already grouped) batch, e.g. from group_by_category."""
+        super().__init__()
+        self.spans = []                       # (category, start, stop), contiguous
+        for i, c in enumerate(categories):
+            if self.spans and self.spans[-1][0] == c:
+                self.spans[-1][2] = i + 1
+            else:
+                assert all(c != s[0] for s in self.spans), "clouds must be grouped by category (use group_by_category)"
+                self.spans.append([c, i, i + 1])
+        parts = {CATEGORIES[c]["num_parts"] for c, _, _ in self.spans}
+        assert len(parts) == 1, "categories of one batch must have the same number of parts (pose tensors are [B,P,...])"
+        self.num_parts = parts.pop()
+        # per-category weights: seed offset by the category's NOCS id so the six weight sets differ
+        self.trackers = torch.nn.ModuleDict(
+            {c: Tracker(make_cfg(c, device=str(device)), seed=seed + 10 * (list(CATEGORIES).index(c) + 1)) for c, _, _ in self.spans})
+
+    @torch.no_grad()
+    def step(self, points, points_mean, last_pose):
+        outs = []
+        for c, a, b in self.spans:
+            outs.append(self.trackers[c].step(points[a:b], points_mean[a:b], {k: v[a:b] for k, v in last_pose.items()}))
+        if len(outs) == 1:
+            return outs[0]
+        return {k: torch.cat([o[k] for o in outs], dim=0) for k in outs[0]}
+
+    def eval_sums(self, gt, pose, out=None, accumulate=False):
+        """One row of sums per category, in span order: [ncat, 5P + 5]."""
+        if out is None:
+            out = torch.zeros(len(self.spans), 5 * self.num_parts + 5, dtype=torch.float32, device=pose["scale"].device)
+        for i, (c, a, b) in enumerate(self.spans):
+            self.trackers[c].eval_sums({k: v[a:b] for k, v in gt.items()}, {k: v[a:b] for k, v in pose.items()},
+                                       out=out[i], accumulate=accumulate)
+        return out
+
+
+def group_by_category(category_ids, names=NOCS_CATEGORIES):
+    """cfg4 assigns category = global trajectory index mod 6 (shard.category_of).  Returns (order, names_sorted):
+    `order` is the stable permutation that groups a shard's trajectories by category, names_sorted the category name
+    of every trajectory after that permutation (MixedTracker's constructor argument)."""
+    order = sorted(range(len(category_ids)), key=lambda i: (category_ids[i], i))
+    return order, [names[category_ids[i]] for i in order]
 
 
 class GraphedStep:
@@ -179,10 +236,17 @@ class GraphedStep:
     Inputs are copied into the graph's static buffers; the returned pose tensors are the graph's
     static outputs (clone them to keep a frame's result across calls)."""
 
-    def __init__(self, tracker, points, points_mean, pose, warmup=2):
+    def __init__(self, tracker, points, points_mean, pose, warmup=2, gt=None):
+        """gt (optional part-pose dict): the graph then also evaluates tracker.eval_sums(gt, new pose) -- the
+        end-of-frame loss / metric reduction -- into self.sums (static), with no extra host launches."""
         from . import _lib
         self.inp = {"points": points.clone(), "points_mean": points_mean.clone(),
                     "pose": {k: v.clone() for k, v in pose.items()}}
+        self.gt = {k: v.clone().float() for k, v in gt.items()} if gt is not None else None
+        self.sums = None
+        if gt is not None:
+            ncat = len(tracker.spans) if hasattr(tracker, "spans") else 1
+            self.sums = torch.zeros(ncat, 5 * tracker.num_parts + 5, dtype=torch.float32, device=points.device)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -194,9 +258,14 @@ class GraphedStep:
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.out = tracker.step(self.inp["points"], self.inp["points_mean"], self.inp["pose"])
+            if self.gt is not None:      # accumulated over the frames replayed since the last self.sums.zero_()
+                self.sums = tracker.eval_sums(self.gt, self.out, out=self.sums, accumulate=True)
         self.launches_per_replay = _lib.launch_count() - n0     # this library's kernels inside the graph
 
-    def __call__(self, points, points_mean, pose):
+    def __call__(self, points, points_mean, pose, gt=None):
+        if gt is not None:
+            for k, v in self.gt.items():
+                v.copy_(gt[k], non_blocking=True)
         self.inp["points"].copy_(points, non_blocking=True)
         self.inp["points_mean"].copy_(points_mean, non_blocking=True)
         for k, v in self.inp["pose"].items():

@@ -102,8 +102,17 @@ int captra_ball_query_multi(int b, int n, int m, int nradii, const float *radii_
                             const int *nsamples_host, const float *new_xyz, const float *xyz,
                             int *const *idx_host_ptrs, captra_stream_t stream);
 
+/* QueryAndGroup (pointnet2_utils.py:271-303) as one call: idx [B,M,K] = ball_query(radius, K, xyz, new_xyz) (idx
+ * must be zeroed by the caller, as for the launcher above) and grouped [B,C,M,K] = group_points(points [B,C,N], idx).
+ * For C <= 8 on a binned cloud the query warp writes its grouped rows itself (one launch set, idx never re-read);
+ * wider rows run the query and the shared-memory-staged gather back to back. */
+int captra_ball_query_group(int b, int n, int m, int c, float radius, int nsample, const float *new_xyz,
+                            const float *xyz, const float *points, int *idx, float *grouped,
+                            captra_stream_t stream);
+
 /* FPS + the gather that always follows it (pointnet_utils.py:225-226): additionally writes
- * new_xyz [B,M,3] = dataset[b, idxs[b,:], :].  new_xyz may be NULL. */
+ * new_xyz [B,M,3] = dataset[b, idxs[b,:], :].  new_xyz may be NULL.  temp may be NULL for n <= 8192 (the running
+ * distances then start at 1e10, as pointnet2_utils.py:27 fills them, and live in registers only). */
 int captra_fps_gather(int b, int n, int m, const float *dataset, float *temp, int *idxs,
                       float *new_xyz, captra_stream_t stream);
 
@@ -198,6 +207,11 @@ int captra_point_mlp_affine(int64_t rows, const float *x, int64_t ldx, int cin, 
                             const void *packed, float *y, int64_t ldy, int col_off, int impl,
                             captra_stream_t stream);
 
+/* y[r, :] <- relu(y[r, :] * scale[r / rows_per_cloud, :] + shift[...]) in place: the unfused form of the
+ * normalise-on-load above, for cloud sizes that are not a multiple of the 128-row tile. */
+int captra_group_norm_relu_rows(int64_t rows, int c, int rows_per_cloud, float *y, int64_t ldy, const float *scale,
+                                const float *shift, captra_stream_t stream);
+
 /* The same launch with the GroupNorm statistics of its OUTPUT fused into the epilogue (in_scale / in_shift may be
  * NULL: plain input).  stats [ceil(rows/128)*4][2][cout] receives, per 32-row block, the column sums and sums of
  * squares of y; captra_group_norm_finalize turns the blocks of each cloud into the per-(cloud, channel) affine of
@@ -239,6 +253,58 @@ int captra_part_fit_st(int b, int p, int n, const int64_t *labels, const float *
                        const float *rotation, const float *given_scale, int sym, float *scale,
                        float *translation, uint8_t *valid, float *rot_out,
                        captra_stream_t stream);
+
+/* The tracker's call of the fit (networks.py:218-232) as one launch: source = pred_nocs [B,P,3,N], target =
+ * points [B,3,N] + points_mean [B,3] for every part, labels [B,N] int64, rotation [B,P,3,3] (given), then
+ *   scale <- valid * scale + (1 - valid) * prev_scale,  translation likewise (fp32, as written there). */
+int captra_part_fit_track(int b, int p, int n, const int64_t *labels, const float *nocs, const float *points,
+                          const float *points_mean, const float *rotation, int sym, const float *prev_scale,
+                          const float *prev_translation, float *scale, float *translation, uint8_t *valid,
+                          captra_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 4b. Per-frame glue between the networks and the fit (Python / ~150 small torch kernels per frame in the
+ *     reference), one launch each.
+ * ---------------------------------------------------------------------------------------- */
+
+/* networks.py:38-41 and :170-187: copy p of cloud b canonicalised by part p's pose,
+ *   out = R^T ((points + mean) - t) / s,   points [B,3,N], points_mean [B,3], rotation [B*P,3,3],
+ *   translation [B*P,3], scale [B*P].  Any of the three outputs may be NULL: out_pm [B*P,N,3] (point-major, what
+ *   the sampling / grouping kernels read), out_cm [B*P,3,N] (the reference's layout, pred_dict['points']),
+ *   out_dup [B*P,N,6] = [xyz, xyz] (the l0 skip of backbones.py:67 with use_xyz_feat). */
+int captra_canonicalize(int b, int p, int n, const float *points, const float *points_mean,
+                        const float *rotation, const float *translation, const float *scale,
+                        float *out_pm, float *out_cm, float *out_dup, captra_stream_t stream);
+
+/* networks.py:44-46 + model.py:458 on the heads' raw point-major outputs seg_raw [B*N, ld_seg] (nseg <= 8 classes)
+ * and nocs_raw [B*N, ld_nocs] (nnocs = 3P channels): labels [B,N] int64 = argmax of softmax (first maximum),
+ * nocs [B,nnocs,N] = sigmoid - 0.5, seg [B,nseg,N] = softmax (may be NULL). */
+int captra_coord_head_post(int b, int n, int nseg, int nnocs, const float *seg_raw, int64_t ld_seg,
+                           const float *nocs_raw, int64_t ld_nocs, int64_t *labels, float *nocs, float *seg,
+                           captra_stream_t stream);
+
+/* blocks.py:181-193 + networks.py:127-141 (diagonal of :200-203) + part_dof_utils.py:124-141: per part p the raw
+ * output of head p on copy p, raw_host_ptrs[p] -> [B*N, ld] point-major (3 channels sym / 6), is turned per point into
+ * a unit vector / 3x3 matrix, averaged over the points with labels == p (default (0,1,0) / identity when there are
+ * none), converted to a rotation (y-axis frame / Gram-Schmidt) and composed: rotation[b,p] = rot_prev[b,p] . dR.
+ * rtvec [B,P,3 or 9] (the averaged prediction) may be NULL. */
+int captra_rot_head_post(int b, int p, int n, int sym, const float *const *raw_host_ptrs, int64_t ld,
+                         const int64_t *labels, const float *rot_prev, float *rotation, float *rtvec,
+                         captra_stream_t stream);
+
+/* Per-frame eval / loss reductions of the tracking loop (model.py:511-561), as sums so that ranks can be
+ * all-reduced:  sums[5p + q], q = 0..4: sum over clouds of sdiff, tdiff, rdiff (degrees; y axis only when sym),
+ * 5deg5cm, 10deg10cm of part p (part_dof_utils.py:40-67, metrics.py:5-47); then sums[5P + 0..4] = number of clouds,
+ * sum over (cloud, class) of mIoU and their number (loss.py:122-134), sum of the l2 NOCS errors over the points the
+ * loss counts and their number (loss.py:42-70).  gt_labels / gt_nocs [B,N] int64 / [B,3,N] may be NULL (those
+ * sums are then 0); seg [B,nseg,N], nocs [B,3P,N], pred_labels [B,N] are the CoordNet predictions.
+ * per_instance [B,P,5] may be NULL; scratch: B*3 floats.  accumulate != 0 adds this frame's sums to what `sums`
+ * holds (the per-batch accumulation of model.py:511-582 over the frames of a trajectory batch). */
+int captra_track_eval(int b, int p, int n, int nseg, int sym, const float *gt_rotation, const float *gt_translation,
+                      const float *gt_scale, const float *rotation, const float *translation, const float *scale,
+                      const float *seg, const float *nocs, const int64_t *pred_labels, const int64_t *gt_labels,
+                      const float *gt_nocs, float *scratch, float *per_instance, float *sums, int accumulate,
+                      captra_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 5. Unit-test doorway for the tcgen05 primitives: D[128,n] = A[128,k] * W[n,k]^T on one CTA

@@ -243,3 +243,24 @@ def test_ball_query_grid_path_bit_exact(kind, n, m, radius, k, futils, oracle, r
     assert np.array_equal(got.cpu().numpy(), want)
     ref = refcu.ball_query(radius, k, dev(pts, cuda), dev(ctr, cuda))
     assert np.array_equal(ref.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("N,M,K,r,C", [(16384, 1024, 64, 0.05, 3), (4096, 512, 32, 0.1, 3), (1000, 100, 16, 0.2, 3),
+                                        (4096, 256, 64, 0.2, 64), (8192, 300, 64, 0.02, 6)])
+def test_ball_query_group_fused(N, M, K, r, C, cuda, oracle):
+    """captra_ball_query_group (QueryAndGroup in one call; the query warp writes the grouped rows itself for few
+    channels) == ball_query then group_points, bit for bit, incl. empty balls (r=0.02: isolated outliers) and a NaN centroid."""
+    from captra_b200 import fused_ops, synthetic
+    from captra_b200.pointnet_lib import pointnet2_utils as futils
+    pts = synthetic.batch_surface_box(2, N, seed=N + K)[0]
+    x = torch.from_numpy(pts).to(cuda)
+    ctr = x[:, torch.randperm(N, generator=torch.Generator().manual_seed(1))[:M]].contiguous()
+    ctr[0, 0] = 10.0                              # far away: empty ball
+    ctr[1, 1, 0] = float("nan")
+    feats = x.transpose(1, 2).contiguous() if C == 3 else torch.randn(2, C, N, device=cuda)
+    idx, grouped = fused_ops.ball_query_group(r, K, x, ctr, feats)
+    want_idx = oracle.ball_query(r, K, pts, ctr.cpu().numpy())
+    assert np.array_equal(idx.cpu().numpy(), want_idx)
+    assert torch.equal(idx, futils.ball_query(r, K, x, ctr))
+    assert torch.equal(grouped, futils.grouping_operation(feats, idx))
+    assert (idx[0, 0] == 0).all() and (idx[1, 1] == 0).all()
