@@ -18,10 +18,12 @@ def canonicalize(points, points_mean, rotation, translation, scale, parts=1, wan
     xyz_pm = torch.empty(B * parts, N, 3, dtype=_f32, device=dev)
     cm = torch.empty(B * parts, 3, N, dtype=_f32, device=dev) if want_cm else None
     dup = torch.empty(B * parts, N, 6, dtype=_f32, device=dev) if want_dup else None
+    # contiguous copies (the root part's slice of a multi-part pose) must stay referenced until the launch is enqueued
+    points, points_mean, rotation, translation, scale = (t.contiguous() for t in (points, points_mean, rotation, translation, scale))
     _lib.call("canonicalize[B=%d,P=%d,N=%d]" % (B, parts, N), _lib.load().captra_canonicalize, B, parts, N,
-              _lib.ptr(points.contiguous(), _f32, "points"), _lib.ptr(points_mean.contiguous(), _f32, "points_mean"),
-              _lib.ptr(rotation.contiguous(), _f32, "rotation"), _lib.ptr(translation.contiguous(), _f32, "translation"),
-              _lib.ptr(scale.contiguous(), _f32, "scale"), xyz_pm.data_ptr(), cm.data_ptr() if want_cm else None,
+              _lib.ptr(points, _f32, "points"), _lib.ptr(points_mean, _f32, "points_mean"),
+              _lib.ptr(rotation, _f32, "rotation"), _lib.ptr(translation, _f32, "translation"),
+              _lib.ptr(scale, _f32, "scale"), xyz_pm.data_ptr(), cm.data_ptr() if want_cm else None,
               dup.data_ptr() if want_dup else None, _lib.stream_ptr(dev), device=dev)
     return xyz_pm, cm, dup
 
@@ -50,8 +52,9 @@ def rot_head_post(raws, labels, rot_prev, sym, want_rtvec=False):
     rotation = torch.empty(B, P, 3, 3, dtype=_f32, device=dev)
     rtvec = torch.empty(B, P, 3 if sym else 9, dtype=_f32, device=dev) if want_rtvec else None
     ptrs = (ctypes.c_void_p * P)(*[_lib.ptr(r, _f32, "raw") for r in raws])
+    rot_prev = rot_prev.contiguous()
     _lib.call("rot_head_post[B=%d,P=%d,N=%d,D=%d]" % (B, P, N, D), _lib.load().captra_rot_head_post, B, P, N, 1 if sym else 0,
-              ptrs, D, _lib.ptr(labels, _i64, "labels"), _lib.ptr(rot_prev.contiguous(), _f32, "rot_prev"),
+              ptrs, D, _lib.ptr(labels, _i64, "labels"), _lib.ptr(rot_prev, _f32, "rot_prev"),
               rotation.data_ptr(), rtvec.data_ptr() if want_rtvec else None, _lib.stream_ptr(dev), device=dev)
     return (rotation, rtvec) if want_rtvec else rotation
 
@@ -64,11 +67,13 @@ def part_fit_track(labels, nocs, points, points_mean, rotation, sym, prev_scale,
     scale = torch.empty(B, P, dtype=_f32, device=dev)
     translation = torch.empty(B, P, 3, 1, dtype=_f32, device=dev)
     valid = torch.empty(B, P, dtype=torch.uint8, device=dev)
+    points, points_mean, rotation, prev_scale, prev_translation = (
+        t.contiguous() for t in (points, points_mean, rotation, prev_scale, prev_translation))      # kept referenced until enqueued
     _lib.call("part_fit_st[B=%d,P=%d,N=%d]" % (B, P, N), _lib.load().captra_part_fit_track, B, P, N,
-              _lib.ptr(labels, _i64, "labels"), _lib.ptr(nocs, _f32, "nocs"), _lib.ptr(points.contiguous(), _f32, "points"),
-              _lib.ptr(points_mean.contiguous(), _f32, "points_mean"), _lib.ptr(rotation.contiguous(), _f32, "rotation"),
-              1 if sym else 0, _lib.ptr(prev_scale.contiguous(), _f32, "prev_scale"),
-              _lib.ptr(prev_translation.contiguous(), _f32, "prev_translation"), scale.data_ptr(), translation.data_ptr(),
+              _lib.ptr(labels, _i64, "labels"), _lib.ptr(nocs, _f32, "nocs"), _lib.ptr(points, _f32, "points"),
+              _lib.ptr(points_mean, _f32, "points_mean"), _lib.ptr(rotation, _f32, "rotation"),
+              1 if sym else 0, _lib.ptr(prev_scale, _f32, "prev_scale"),
+              _lib.ptr(prev_translation, _f32, "prev_translation"), scale.data_ptr(), translation.data_ptr(),
               valid.data_ptr(), _lib.stream_ptr(dev), device=dev)
     return scale, translation, valid.bool()
 
@@ -89,9 +94,10 @@ def track_eval(gt, pose, sym, pred=None, gt_labels=None, gt_nocs=None, per_insta
         seg, nocs, labels = pred["seg"], pred["nocs"], pred["labels"]
         nseg, n = seg.shape[1], seg.shape[2]
     scratch = torch.empty(max(B, 1) * 3, dtype=_f32, device=dev)
-    g = lambda t: _lib.ptr(t.contiguous(), _f32, "pose")
+    keep = [t.contiguous() for t in (gt["rotation"], gt["translation"], gt["scale"], pose["rotation"], pose["translation"], pose["scale"])]
+    g = lambda i: _lib.ptr(keep[i], _f32, "pose")       # `keep` holds any contiguous copy until the launch is enqueued
     _lib.call("track_eval[B=%d,P=%d,N=%d]" % (B, P, n), _lib.load().captra_track_eval, B, P, n, nseg, 1 if sym else 0,
-              g(gt["rotation"]), g(gt["translation"]), g(gt["scale"]), g(pose["rotation"]), g(pose["translation"]), g(pose["scale"]),
+              g(0), g(1), g(2), g(3), g(4), g(5),
               _lib.ptr(seg, _f32, "seg"), _lib.ptr(nocs, _f32, "nocs"), _lib.ptr(labels, _i64, "labels"),
               _lib.ptr(gt_labels, _i64, "gt_labels"), _lib.ptr(gt_nocs, _f32, "gt_nocs"), scratch.data_ptr(),
               per.data_ptr() if per is not None else None, sums.data_ptr(), 1 if accumulate else 0, _lib.stream_ptr(dev), device=dev)
