@@ -452,8 +452,57 @@ def reference_gpu_pass(dev, flush, B=32):
     both("gather_points[C=128,M=512]", lambda: ref_cuda.gather_operation(feats, idx), lambda: ours.gather_operation(feats, idx))
     both("three_nn[n=4096,m=512]", lambda: ref_cuda.three_nn(pts, ctr), lambda: ours.three_nn(pts, ctr))
     both("three_interpolate[C=128,m=512,n=4096]", lambda: ref_cuda.three_interpolate(f512, i3, w3), lambda: ours.three_interpolate(f512, i3, w3))
-    return {"what": "reference kernels (network/models/pointnet_lib/src/*_gpu.cu compiled unmodified for sm_100) vs libcaptra_ops.so, same GPU, same inputs",
-            "ops": rows}
+    out = {"what": "reference kernels (network/models/pointnet_lib/src/*_gpu.cu compiled unmodified for sm_100) vs libcaptra_ops.so, same GPU, same inputs",
+           "ops": rows}
+    try:
+        out["frame"] = reference_gpu_frame(dev, flush)
+    except Exception as e:  # noqa: BLE001
+        out["frame"] = {"error": str(e).splitlines()[0][:200]}
+    return out
+
+
+def reference_gpu_frame(dev, flush, category="bottle", B=32, reps=5):
+    """The reference's WHOLE GPU path for one tracking frame on this box: its own CUDA kernels (oracle/_ref), its own
+    pointnet2_utils.py / pointnet_utils.py / backbones.py / blocks.py / networks.py torch modules (cuDNN / cuBLAS fp32, TF32
+    off) and its pose fit with torch.svd on the CPU (oracle/_ref/pyref, unmodified) -- the "kernel to beat" at frame level."""
+    if not os.path.isdir(PYREF):
+        return {"unavailable": "oracle/_ref/pyref not built"}
+    from captra_b200 import track
+    from oracle import ref_pointnet2_cuda
+    saved = {k: sys.modules.get(k) for k in ("pointnet2_cuda", "pointnet_lib", "pointnet_lib.pointnet2_utils", "pose_utils", "pose_utils.procrustes",
+                                             "pose_utils.pose_fit", "procrustes", "pose_fit")}
+    for k in saved:
+        sys.modules.pop(k, None)
+    sys.modules["pointnet2_cuda"] = ref_pointnet2_cuda
+    sys.path[:0] = [os.path.join(PYREF, "network", "models"), os.path.join(PYREF, "pose_utils"), PYREF]
+    try:
+        import networks as RN
+        import pointnet_utils as RPU
+        assert RPU.CUDA and RN.__file__.startswith(PYREF)
+        cfg = track.make_cfg(category, device=str(dev))
+        P = cfg["num_parts"]
+        npcs_net = track.init_weights(RN.CoordNet(cfg), 0).to(dev).eval()
+        net = track.init_weights(RN.PartCanonNet(cfg), 1).to(dev).eval()
+        b = track.synthetic_track_batch(B, category, n=4096, seed=0)
+        p, m = torch.from_numpy(b["points"]).to(dev), torch.from_numpy(b["points_mean"]).to(dev)
+        pose = {k: torch.from_numpy(v).to(dev) for k, v in b["pose"].items()}
+
+        def frame():
+            with torch.no_grad(), torch.device(dev):      # model.py:454-476 (torch 2.x needs the default device: networks.py:127-128)
+                canon = {k: pose[k][:, 0] for k in ("rotation", "translation", "scale")}
+                pred = npcs_net({"points": p, "points_mean": m, "canon_pose": canon})
+                labels = torch.max(pred["seg"], dim=-2)[1]
+                return net({"points": p, "points_mean": m, "state": {"part": pose}, "pred_labels": labels,
+                            "pred_nocs": pred["nocs"].reshape(B, P, 3, -1)}, test_mode=True)["part"]
+        us = _timed_us(frame, flush, reps)
+        return {"what": "reference GPU path, %s, %d x 4096 pts: its own kernels + torch modules + CPU torch.svd" % (category, B),
+                "ms_per_step": us * 1e-3, "frames_per_s": B / us * 1e6}
+    finally:
+        for k in ("networks", "pointnet_utils", "backbones", "blocks", "pointnet2_cuda", "pointnet_lib", "pointnet_lib.pointnet2_utils"):
+            sys.modules.pop(k, None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
 
 
 def svd_pass(dev, flush):

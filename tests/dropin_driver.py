@@ -78,7 +78,10 @@ for category in ("bottle", "laptop"):
     b = track.synthetic_track_batch(2, category, n=4096, seed=0)
     p, m = torch.from_numpy(b["points"]).to(dev), torch.from_numpy(b["points_mean"]).to(dev)
     pose = {k: torch.from_numpy(v).to(dev) for k, v in b["pose"].items()}
-    with torch.no_grad():          # model.py:454-476 with the reference's modules
+    # torch 1.6 (the reference's pin) let a CPU tensor be indexed by CUDA indices (networks.py:127-128 builds `eye_mat`
+    # on the CPU and indexes it with CUDA labels); torch 2.x does not, so factory calls default to the GPU here --
+    # an environment setting, the reference's code is untouched
+    with torch.no_grad(), torch.device(dev):          # model.py:454-476 with the reference's modules
         canon = {k: pose[k][:, trk.root] for k in ("rotation", "translation", "scale")}
         pred = npcs_net({"points": p, "points_mean": m, "canon_pose": canon})
         labels = torch.max(pred["seg"], dim=-2)[1]

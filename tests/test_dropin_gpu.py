@@ -35,6 +35,6 @@ def test_reference_python_runs_on_the_dropin(mode, cuda):
         assert f["labels_equal"], category
         assert f["nocs_max_abs"] < 1e-4, (category, f)
         assert f["rotation_max_abs"] < 1e-4, (category, f)
-        assert f["scale_max_abs"] < 2e-3 and f["translation_max_abs"] < 2e-3, (category, f)   # ill-conditioned with raw random weights (see golden_util.pose_tolerance)
+        assert f["scale_max_abs"] < 2e-4 and f["translation_max_abs"] < 2e-4, (category, f)   # ill-conditioned with raw random weights (golden_util.pose_tolerance); measured 3e-5
         if mode == "a":
             assert f["procrustes_module"] == "captra_b200.pose_utils.procrustes"

@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True)
 def _no_tf32():
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
 
 
 def _pose(B, P, gen, dev):
