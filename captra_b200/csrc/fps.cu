@@ -18,6 +18,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace captra {
 
@@ -164,6 +165,158 @@ fps_stream_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cluster variant for clouds above one CTA's register capacity (8192 points) -- BASELINE cfg5's 16384 -> 4096 and
+// the data loader's 20480 -> 4096 resample (datasets/data_utils.py:138-158).  The reference (and fps_stream_kernel)
+// re-read the cloud and its distances from L2 in every one of the M-1 rounds.  Here a thread-block CLUSTER of CS
+// CTAs owns a cloud: every point and its running distance live in registers (PPT per thread, CS*NT*PPT >= n), and a
+// round is
+//   PPT distance updates -> warp arg-max (two redux.sync) -> the winning lane writes its warp's record
+//   {dist, key, x, y, z} into EVERY CTA of the cluster (distributed shared memory, st.shared::cluster)
+//   -> ONE barrier.cluster (release/acquire) -> every warp re-reduces the CS*32 records redundantly.
+// The winner's coordinates travel inside the record, so the loop touches no global memory at all.  Same 64-bit
+// key as fps_reg_kernel => the reference's tie rule bit for bit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int NT, int PPT, int CS>
+__global__ void __launch_bounds__(NT)
+fps_cluster_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
+                   float *__restrict__ temp, int *__restrict__ idxs, float *__restrict__ new_xyz) {
+    constexpr int NW = NT / 32, NREC = CS * NW;           // records per round: one per warp of the cluster
+    static_assert(NREC <= 256, "at most eight records per lane in the final reduction");
+    __shared__ uint32_t rec[2][5][NREC];                  // [round parity][dist, key, x, y, z][cluster warp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t crank = cluster_ctarank();
+    const int b = blockIdx.x / CS;
+    const float *cloud = dataset + (size_t)b * n * 3;
+    float *tmp = temp ? temp + (size_t)b * n : nullptr;
+    int *out = idxs + (size_t)b * m;
+    float *oxyz = new_xyz ? new_xyz + (size_t)b * m * 3 : nullptr;
+    const int ref_mask = (1 << ref_bits) - 1;
+    const int ref_shift = ref_bits ? 32 - ref_bits : 31;
+    const bool writer = crank == 0 && tid == 0;
+
+    float x[PPT], y[PPT], z[PPT], t[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int k = (j * CS + (int)crank) * NT + tid;     // consecutive threads <-> consecutive points
+        const bool ok = k < n;
+        x[j] = ok ? __ldg(cloud + (size_t)k * 3 + 0) : 0.f;
+        y[j] = ok ? __ldg(cloud + (size_t)k * 3 + 1) : 0.f;
+        z[j] = ok ? __ldg(cloud + (size_t)k * 3 + 2) : 0.f;
+        t[j] = ok ? (tmp ? tmp[k] : 1e10f) : -INFINITY;
+    }
+    float ox = __ldg(cloud + 0), oy = __ldg(cloud + 1), oz = __ldg(cloud + 2);
+    if (writer) {
+        out[0] = 0;
+        if (oxyz) { oxyz[0] = ox; oxyz[1] = oy; oxyz[2] = oz; }
+    }
+    // this warp's record slot in every CTA of the cluster
+    const uint32_t slot_addr = (uint32_t)__cvta_generic_to_shared(&rec[0][0][crank * NW + warp]);
+    cluster_sync_all();                                   // every CTA of the cluster is resident before remote stores
+
+    for (int r = 1; r < m; ++r) {
+        float tm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const float d = sqdist_ref(x[j], y[j], z[j], ox, oy, oz);
+            t[j] = fminf(d, t[j]);
+            tm = fmaxf(tm, t[j]);
+        }
+        const unsigned um = ordered_bits(tm);
+        const unsigned wm = __reduce_max_sync(kFull, um);
+        unsigned tb = 0;
+        float bx = 0.f, by = 0.f, bz = 0.f;
+        if (um == wm) {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+                const unsigned key = tie_key((j * CS + (int)crank) * NT + tid, ref_mask, ref_shift);
+                if (t[j] == tm && key > tb) { tb = key; bx = x[j]; by = y[j]; bz = z[j]; }
+            }
+        }
+        const unsigned wt = __reduce_max_sync(kFull, tb);
+        if (um == wm && tb == wt) {                        // exactly one lane: keys are unique
+            const uint32_t po = slot_addr + (uint32_t)((r & 1) * 5 * NREC) * 4u;
+            const uint32_t w[5] = {wm, wt, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz)};
+#pragma unroll
+            for (int c = 0; c < CS; ++c) {
+                const uint32_t ra = mapa_shared(po, (uint32_t)c);     // the same slot in CTA c of the cluster
+#pragma unroll
+                for (int q = 0; q < 5; ++q) st_cluster_u32(ra + (uint32_t)(q * NREC) * 4u, w[q]);
+            }
+        }
+        cluster_sync_all();
+        // every warp reduces the NREC records redundantly (lane l: records l, l+32, ...)
+        unsigned qm = 0, qt = 0;
+        int qi = 0;
+#pragma unroll
+        for (int i = 0; i < (NREC + 31) / 32; ++i) {
+            const int e = lane + 32 * i;
+            if (e < NREC) {
+                const unsigned em = rec[r & 1][0][e], et = rec[r & 1][1][e];
+                if (em > qm || (em == qm && et > qt)) { qm = em; qt = et; qi = e; }
+            }
+        }
+        const unsigned bm = __reduce_max_sync(kFull, qm);
+        const unsigned bt = __reduce_max_sync(kFull, qm == bm ? qt : 0u);
+        const unsigned who = __ballot_sync(kFull, qm == bm && qt == bt);
+        const int src = __ffs(who) - 1;
+        const int wi = __shfl_sync(kFull, qi, src);
+        ox = __uint_as_float(rec[r & 1][2][wi]);
+        oy = __uint_as_float(rec[r & 1][3][wi]);
+        oz = __uint_as_float(rec[r & 1][4][wi]);
+        if (writer) {
+            out[r] = (int)((~bt) & 0x3fffffu);
+            if (oxyz) { oxyz[r * 3 + 0] = ox; oxyz[r * 3 + 1] = oy; oxyz[r * 3 + 2] = oz; }
+        }
+    }
+    if (tmp) {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const int k = (j * CS + (int)crank) * NT + tid;
+            if (k < n) tmp[k] = t[j];
+        }
+    }
+    cluster_sync_all();                                   // no CTA exits while a peer may still address its shared memory
+}
+
+template <int NT, int PPT, int CS>
+static int launch_fps_cluster(int b, int n, int m, int ref_bits, const float *dataset, float *temp,
+                              int *idxs, float *new_xyz, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)b * CS);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CAPTRA_CUDA(cudaLaunchKernelEx(&cfg, fps_cluster_kernel<NT, PPT, CS>, n, m, ref_bits, dataset, temp, idxs, new_xyz));
+    CAPTRA_CHECK_LAUNCH("furthest_point_sampling(cluster)");
+    return CAPTRA_OK;
+}
+
 template <int NT, int PPT>
 static int launch_fps_reg(int b, int n, int m, int ref_bits, const float *dataset, float *temp,
                           int *idxs, float *new_xyz, cudaStream_t stream) {
@@ -188,7 +341,7 @@ extern "C" int captra_fps_gather(int b, int n, int m, const float *dataset, floa
     CAPTRA_REQUIRE(n >= 1, "fps: empty cloud with m > 0");
     CAPTRA_REQUIRE(n < (1 << 22), "fps: n=%d exceeds the 2^22 key width", n);
     CAPTRA_REQUIRE(dataset && idxs, "fps: null pointer");
-    CAPTRA_REQUIRE(temp || n <= 8192, "fps: clouds above 8192 points keep their running distances in `temp` (must not be NULL)");
+    CAPTRA_REQUIRE(temp || n <= 32768, "fps: clouds above 32768 points keep their running distances in `temp` (must not be NULL)");
     // block = min(1024, 2^floor(log2 n)) (cuda_utils.h:10-14); exact integer log2 here -- the
     // reference's log()/log() quotient evaluates to the same integer for every n < 2^22
     // (checked exhaustively in tests/test_oracle.py).
@@ -201,6 +354,14 @@ extern "C" int captra_fps_gather(int b, int n, int m, const float *dataset, floa
     if (n <= 2048) return launch_fps_reg<256, 8>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
     if (n <= 4096) return launch_fps_reg<512, 8>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
     if (n <= 8192) return launch_fps_reg<1024, 8>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+    // above one CTA's registers: a cluster of 4 / 8 CTAs per cloud (CAPTRA_FPS_CLUSTER=0 forces the streaming kernel)
+    static const bool use_cluster = [] { const char *e = getenv("CAPTRA_FPS_CLUSTER"); return !e || atoi(e) != 0; }();
+    if (use_cluster && (int64_t)b * 8 < (1LL << 31)) {
+        // 4 points per thread: 16 data registers, so the 64-register budget of a 1024-thread CTA holds without spills
+        if (n <= 16384) return launch_fps_cluster<1024, 4, 4>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+        if (n <= 32768) return launch_fps_cluster<1024, 4, 8>(b, n, m, ref_bits, dataset, temp, idxs, new_xyz, s);
+    }
+    CAPTRA_REQUIRE(temp, "fps: the streaming kernel keeps its running distances in `temp` (must not be NULL)");
     fps_stream_kernel<1024><<<b, 1024, 0, s>>>(n, m, ref_bits, dataset, temp, idxs, new_xyz);
     CAPTRA_CHECK_LAUNCH("furthest_point_sampling(stream)");
     return CAPTRA_OK;

@@ -14,7 +14,7 @@ def fps_gather(xyz, npoint):
     B, N, _ = xyz.shape
     idx = torch.empty(B, npoint, dtype=_i32, device=xyz.device)
     new_xyz = torch.empty(B, npoint, 3, dtype=_f32, device=xyz.device)
-    temp = torch.full((B, N), 1e10, dtype=_f32, device=xyz.device) if N > 8192 else None   # registers below that
+    temp = torch.full((B, N), 1e10, dtype=_f32, device=xyz.device) if N > 32768 else None   # registers (one CTA or a cluster) below that
     _lib.call("fps_gather[B=%d,N=%d,M=%d]" % (B, N, npoint), _lib.load().captra_fps_gather, B, N, npoint,
               _lib.ptr(xyz, _f32, "xyz"), temp.data_ptr() if temp is not None else None, idx.data_ptr(), new_xyz.data_ptr(),
               _lib.stream_ptr(xyz.device), device=xyz.device)

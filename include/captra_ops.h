@@ -111,8 +111,9 @@ int captra_ball_query_group(int b, int n, int m, int c, float radius, int nsampl
                             captra_stream_t stream);
 
 /* FPS + the gather that always follows it (pointnet_utils.py:225-226): additionally writes
- * new_xyz [B,M,3] = dataset[b, idxs[b,:], :].  new_xyz may be NULL.  temp may be NULL for n <= 8192 (the running
- * distances then start at 1e10, as pointnet2_utils.py:27 fills them, and live in registers only). */
+ * new_xyz [B,M,3] = dataset[b, idxs[b,:], :].  new_xyz may be NULL.  temp may be NULL for n <= 32768 (the running
+ * distances then start at 1e10, as pointnet2_utils.py:27 fills them, and live in registers only: one CTA per cloud
+ * up to 8192 points, a thread-block cluster of 4 / 8 CTAs exchanging through distributed shared memory above). */
 int captra_fps_gather(int b, int n, int m, const float *dataset, float *temp, int *idxs,
                       float *new_xyz, captra_stream_t stream);
 

@@ -264,3 +264,22 @@ def test_ball_query_group_fused(N, M, K, r, C, cuda, oracle):
     assert torch.equal(idx, futils.ball_query(r, K, x, ctr))
     assert torch.equal(grouped, futils.grouping_operation(feats, idx))
     assert (idx[0, 0] == 0).all() and (idx[1, 1] == 0).all()
+
+
+@pytest.mark.parametrize("n,m,kind", [(16384, 1024, "surface"), (12000, 700, "tiled"), (32768, 300, "uniform"), (20480, 4096, "tiled"),
+                                       (40000, 200, "uniform")])
+def test_fps_cluster_path(n, m, kind, oracle, cuda):
+    """Clouds above 8192 points: a thread-block cluster per cloud, records exchanged through distributed shared memory
+    (n <= 32768), the streaming kernel beyond; no caller scratch (fused_ops.fps_gather).  Bit-exact incl. exhausted
+    duplicates (tiled: as the data loader pads small crops, nocs_data_process.py:105-106)."""
+    from captra_b200 import fused_ops
+    if kind == "surface":
+        pts = synthetic.batch_surface_box(3, n, seed=n)[0]
+    elif kind == "tiled":
+        pts = synthetic.batch_tiled(2, n, 3000, seed=n)
+    else:
+        pts = synthetic.batch_uniform(2, n, seed=n)
+    idx, new_xyz = fused_ops.fps_gather(dev(pts, cuda), m)
+    want = oracle.furthest_point_sample(pts, m)
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert np.array_equal(new_xyz.cpu().numpy(), np.take_along_axis(pts, want.astype(np.int64)[..., None], 1))
