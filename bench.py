@@ -529,6 +529,26 @@ def svd_pass(dev, flush):
     return out
 
 
+def crop_pass(dev, flush):
+    """the data-side crop of one frame (B = 1, as in nocs_otf tracking) on the device --
+    back-projection + ball crop + 5*4096 thinning + FPS 20480 -> 4096 (nocs_data_process.py:148-164) -- ms per frame,
+    and the FPS kernels alone at the large-cloud shapes (cluster variant)."""
+    from captra_b200 import data_crop, fused_ops, synthetic
+    out = {}
+    for name, kw, off, radius in (("20480->4096 (thinned crop)", dict(seed=1, obj_radius=0.25, obj_depth=0.6), 0.1, 0.3),
+                                  ("small crop tiled to 4096", dict(seed=3, obj_radius=0.05, obj_depth=1.2), 0.02, 0.06)):
+        depth, mask, c, K = synthetic.depth_scene(**kw)
+        d, m = torch.from_numpy(depth).to(dev), torch.from_numpy(mask).to(dev)
+        center = c + np.array([0.0, 0.0, off])
+        us = _timed_us(lambda: data_crop.crop_ball_from_depth_image(d, m, center, radius, cam_intrinsics=K, num_points=4096), flush, 5)
+        out[name] = {"ms_per_frame": us * 1e-3}
+    for B, N, M in ((1, 20480, 4096), (64, 16384, 4096), (32, 4096, 512)):
+        x = torch.from_numpy(synthetic.batch_surface_box(B, N, seed=1)[0]).to(dev)
+        us = _timed_us(lambda: fused_ops.fps_gather(x, M), flush, 3)
+        out["fps[B=%d,%d->%d]" % (B, N, M)] = {"us": us, "us_per_round": us / (M - 1)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -759,6 +779,10 @@ def main():
                 extras["svd"] = svd_pass(dev, flush)
             except Exception as e:  # noqa: BLE001
                 extras["svd"] = {"error": str(e).splitlines()[0][:200]}
+            try:
+                extras["crop"] = crop_pass(dev, flush)
+            except Exception as e:  # noqa: BLE001
+                extras["crop"] = {"error": str(e).splitlines()[0][:200]}
 
     overflow = mlp.f16_overflowed() if mlp.DEFAULT_IMPL == 2 else None
     if rank != 0:

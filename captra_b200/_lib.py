@@ -52,6 +52,9 @@ SIGNATURES = {
     "captra_coord_head_post": [c_int] * 4 + [_P, c_i64, _P, c_i64, _P, _P, _P, _P],
     "captra_rot_head_post": [c_int] * 4 + [_P, c_i64, _P, _P, _P, _P, _P],
     "captra_track_eval": [c_int] * 5 + [_P] * 14 + [c_int, _P],
+    "captra_crop_select": [c_int, c_int, _P, _P, _P, _P, _P, ctypes.c_double, c_int] + [_P] * 8,
+    "captra_crop_subset": [c_int, c_int, _P, _P, _P, _P],
+    "captra_crop_gather": [c_int, c_int] + [_P] * 10,
     "captra_part_fit_st": [c_int] * 3 + [_P, _P] + [_P] + [c_i64] * 4 + [_P] + [c_i64] * 4 + [_P, _P, c_int, _P, _P, _P, _P, _P],
 }
 OTHER_SYMBOLS = ["captra_last_error", "captra_abi_version", "captra_launch_count", "captra_mlp_pack_bytes"]

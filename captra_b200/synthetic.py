@@ -100,3 +100,31 @@ def pose_fit_case(b, p, n, seed=0, nocs_noise=0.01, sym=False):
         for pi in range(p):
             nocs[bi, pi] = ((cam_pts - t[bi, pi]) @ R[bi, pi]) / s[bi, pi] + rng.normal(scale=nocs_noise, size=(n, 3))
     return dict(cam=cam, labels=labels, nocs=nocs, R=R, s=s, t=t)
+
+
+def depth_scene(seed=0, obj_radius=0.12, obj_depth=0.8, height=480, width=640, holes=0.02,
+                intrinsics=((591.0125, 0, 322.525), (0, 590.16775, 244.11084), (0, 0, 1))):
+    """A synthetic depth frame for the data-side crop (nocs_data_process.py:148-164): a sphere of `obj_radius` metres
+    whose centre is `obj_depth` metres in front of the camera (slightly off-axis), in front of a noisy back wall at
+    ~2 m; integer millimetres as a depth sensor gives them, `holes` of the pixels without measurement (0).
+    Returns depth [H,W] float32 (mm), mask [H,W] int32 (1 = object), the sphere centre in the reference's camera
+    frame (z negative, nocs_utils.py:29) and the intrinsics."""
+    rng = np.random.default_rng(seed)
+    K = np.array(intrinsics, dtype=np.float64)
+    Kinv = np.linalg.inv(K)
+    rows, cols = np.mgrid[0:height, 0:width]
+    uv = np.stack([cols.ravel(), height - rows.ravel(), np.ones(height * width)])
+    ray = (Kinv @ uv).T                                   # (x, y, 1): the point at depth d is (x d, y d, -d)
+    ray[:, 2] = -1.0
+    c = np.array([0.05 * rng.normal(), 0.04 * rng.normal(), -obj_depth])
+    a = (ray * ray).sum(1)
+    bq = -2.0 * ray @ c
+    cq = c @ c - obj_radius ** 2
+    disc = bq * bq - 4 * a * cq
+    hit = disc > 0
+    d = np.full(height * width, 2.0) + 0.01 * rng.normal(size=height * width)
+    d[hit] = (-bq[hit] - np.sqrt(disc[hit])) / (2 * a[hit])
+    depth = np.round(d * 1000.0).astype(np.float32)
+    depth[rng.random(height * width) < holes] = 0.0
+    mask = hit.astype(np.int32)
+    return depth.reshape(height, width), mask.reshape(height, width), c, K

@@ -308,6 +308,32 @@ int captra_track_eval(int b, int p, int n, int nseg, int sym, const float *gt_ro
                       captra_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * 4c. Data-side crop of a frame on the device (datasets/nocs_data/nocs_data_process.py:92-109,148-164,
+ *     nocs_utils.py:5-33, data_utils.py:138-158): numpy on the host in the reference.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Back-project the depth window [r0..r1] x [c0..c1] (window_host = {r0, c0, r1, c1}, inclusive; depth [H,W] fp32 in
+ * millimetres, 0 = no measurement; mask [H,W] int32 or NULL), test every point against the ball around center_host
+ * (3 doubles) and select, in row-major pixel order, the points of the first radius max(radius, .05) * 1.10^i, i < 10,
+ * that holds at least ten of them (grow != 0; only i = 0 otherwise) -- or every back-projected point when even the
+ * last radius is empty.  kinv_host: the 3x3 inverse intrinsics (row-major doubles).
+ * Outputs: meta[0] = n, meta[1] = selected level threshold, meta[2] = index of the radius used; pts [n,3] fp64,
+ * pmask [n], pix [n] (row * W + col).  Scratch: level [window pixels] bytes, hist [rows * 11], row_off [rows].
+ * pts / pmask / pix must hold one entry per window pixel (n is only known on the device). */
+int captra_crop_select(int h, int w, const float *depth, const int *mask, const int *window_host,
+                       const double *kinv_host, const double *center_host, double radius, int grow,
+                       uint8_t *level, int *hist, int *row_off, int *meta, double *pts, int *pmask, int *pix,
+                       captra_stream_t stream);
+/* cloud[j] = float(pts[(sel ? sel[j] : j) % n]), j < count: the tiled (nocs_data_process.py:105-106) and, with
+ * sel = a permutation prefix, randomly thinned (data_utils.py:147-149) list FPS then runs on. */
+int captra_crop_subset(int n, int count, const int64_t *sel, const double *pts, float *cloud, captra_stream_t stream);
+/* out[j] = selected entry (sel ? sel[q] : q) % n with q = fps_idx ? fps_idx[j] : j -- points (fp64), mask values,
+ * index into the selected list, pixel index. */
+int captra_crop_gather(int n, int count, const int *fps_idx, const int64_t *sel, const double *pts, const int *pmask,
+                       const int *pix, double *out_pts, int *out_mask, int64_t *out_idx, int *out_pix,
+                       captra_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * 5. Unit-test doorway for the tcgen05 primitives: D[128,n] = A[128,k] * W[n,k]^T on one CTA
  *    (terms = 1: single-pass TF32, 3: 3xTF32), and the clock64 phase stamps the fused kernel
  *    records when CAPTRA_TC_DBG has bit 32/128 set.  Not used by the product path.

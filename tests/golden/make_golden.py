@@ -245,7 +245,75 @@ def golden_frame():
     print("frame.npz", len(out), "arrays", os.path.getsize(os.path.join(HERE, "frame.npz")) // 1024, "KiB")
 
 
+sys.path.insert(0, os.path.dirname(HERE))
+from golden_util import CROP_CASES  # noqa: E402
+
+
+def golden_crop():
+    """datasets/nocs_data/nocs_data_process.py:148-164 crop_ball_from_depth_image (-> crop_ball_from_pts :92-109,
+    get_proj_corners :129-143, nocs_utils.backproject, data_utils.farthest_point_sample :138-158) -- the REFERENCE's own
+    functions, run here on synthetic depth frames (captra_b200.synthetic.depth_scene).  Their CUDA branch is taken
+    (torch.cuda.is_available patched to True) with the FPS kernel call replaced by oracle/cpu_ref (the kernel's
+    semantics); the permutation numpy's global RNG hands out is recorded so the device path can be fed the same one.
+    trimesh / matplotlib / pylab (not installed; imported by data_utils.py for unrelated code) are stubbed."""
+    import importlib.abc
+    import importlib.machinery
+    import types
+    from unittest import mock
+
+    class _Stub(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return mock.MagicMock()
+
+    class Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        P = ("trimesh", "matplotlib", "mpl_toolkits", "pylab")
+
+        def find_spec(self, name, path, target=None):
+            if name.split(".")[0] in self.P:
+                return importlib.machinery.ModuleSpec(name, self, is_package=True)
+
+        def create_module(self, spec):
+            m = _Stub(spec.name)
+            m.__path__ = []
+            return m
+
+        def exec_module(self, module):
+            pass
+    sys.meta_path.insert(0, Finder())
+    sys.path[:0] = [os.path.join(REF, "datasets", "nocs_data"), os.path.join(REF, "datasets")]
+    import nocs_data_process as NDP
+    import data_utils as DU
+    DU.farthest_point_sample_cuda = lambda xyz, npoint: T(cpu_ref.furthest_point_sample(np.ascontiguousarray(xyz.numpy()), npoint)).long()
+    out = {}
+    for name, (scene, off, radius, num_points) in CROP_CASES.items():
+        depth, mask, c, K = synthetic.depth_scene(**scene)
+        center = c + np.array(off)
+        perms = []
+        real_perm = np.random.permutation
+
+        def rec_perm(n):
+            p = real_perm(n)
+            perms.append(p)
+            return p
+        np.random.seed(100 + scene["seed"])
+        with mock.patch.object(torch.cuda, "is_available", return_value=True), mock.patch.object(np.random, "permutation", rec_perm):
+            pts, obj_mask = NDP.crop_ball_from_depth_image(depth, mask, center.copy(), radius, cam_intrinsics=K,
+                                                           num_points=num_points, device="cpu")
+        assert len(perms) <= 1
+        out[name + "/pts"] = pts
+        out[name + "/obj_mask"] = obj_mask.astype(np.int32)
+        out[name + "/center"] = center
+        if perms:
+            out[name + "/perm_len"] = np.array(len(perms[0]))
+            out[name + "/perm_head"] = perms[0][:5 * num_points].astype(np.int32)
+        print(name, "points", pts.shape, "object fraction %.2f" % obj_mask.mean(), "perm" if perms else "")
+    np.savez_compressed(os.path.join(HERE, "crop.npz"), **out)
+    print("crop.npz", len(out), "arrays", os.path.getsize(os.path.join(HERE, "crop.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["procrustes", "ops_index", "backbone", "frame"]
+    which = sys.argv[1:] or ["procrustes", "ops_index", "backbone", "frame", "crop"]
     for name in which:
         globals()["golden_" + name]()

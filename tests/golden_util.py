@@ -12,6 +12,15 @@ FEAT_STRIDE = 16
 CATEGORY = {"bottle": "bottle", "camera": "camera", "laptop": "laptop", "bottle_t": "bottle", "laptop_t": "laptop"}
 _cache = {}
 
+CROP_CASES = {   # name -> (scene kwargs, centre offset from the sphere centre [m], crop radius [m], num_points)
+    "large_thinned": (dict(seed=1, obj_radius=0.25, obj_depth=0.6), (0.0, 0.0, 0.1), 0.3, 4096),      # > 5 * 4096 points: random subset, then FPS
+    "medium": (dict(seed=2, obj_radius=0.12, obj_depth=0.8), (0.0, 0.0, 0.05), 0.15, 4096),          # 4096 < n <= 20480: plain FPS
+    "small_tiled": (dict(seed=3, obj_radius=0.05, obj_depth=1.2), (0.0, 0.0, 0.02), 0.06, 4096),      # n < 4096: idx doubled until >= 4096
+    "radius_grows": (dict(seed=4, obj_radius=0.1, obj_depth=0.9), (0.0, 0.0, 0.165), 0.05, 1024),     # < 10 points at first: radius *= 1.10
+    "take_all": (dict(seed=5, obj_radius=0.1, obj_depth=0.9), (0.0, 0.0, 0.45), 0.05, 512),           # still empty after ten tries: every point of the window
+    "no_resample": (dict(seed=6, obj_radius=0.12, obj_depth=0.8), (0.0, 0.0, 0.05), 0.1, None),       # num_points=None: the ball, no FPS
+}
+
 
 def load():
     if "g" not in _cache:
