@@ -172,9 +172,9 @@ fps_stream_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
 // re-read the cloud and its distances from L2 in every one of the M-1 rounds.  Here a thread-block CLUSTER of CS
 // CTAs owns a cloud: every point and its running distance live in registers (PPT per thread, CS*NT*PPT >= n), and a
 // round is
-//   PPT distance updates -> warp arg-max (two redux.sync) -> the winning lane writes its warp's record
-//   {dist, key, x, y, z} into EVERY CTA of the cluster (distributed shared memory, st.shared::cluster)
-//   -> ONE barrier.cluster (release/acquire) -> every warp re-reduces the CS*32 records redundantly.
+//   PPT distance updates -> warp arg-max (two redux.sync) -> CTA arg-max -> the CTA's record {dist, key, x, y, z}
+//   goes into EVERY CTA of the cluster (distributed shared memory, st.shared::cluster + a remote mbarrier arrive)
+//   -> every warp re-reduces the CS records redundantly (see the kernel for the synchronisation).
 // The winner's coordinates travel inside the record, so the loop touches no global memory at all.  Same 64-bit
 // key as fps_reg_kernel => the reference's tie rule bit for bit.
 // ------------------------------------------------------------------------------------------------
@@ -194,14 +194,39 @@ __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_init_cl(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_remote_arrive_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 
+// Round structure: (1) warp arg-max -> per-warp record in LOCAL shared memory -> __syncthreads -> warp 0 reduces the
+// CTA's NW records; (2) one lane writes the CTA record {dist, key, x, y, z} into every CTA of the cluster
+// (st.shared::cluster) and arrives, with release at cluster scope, on that CTA's mbarrier -- CS remote arrivals per
+// barrier and round, from ONE thread per CTA (the hardware cluster barrier, which every warp of the cluster has to
+// reach, measured 2-3 us per round here); (3) warp 0 waits on the local mbarrier (acquire.cluster), __syncthreads hands
+// the records to the other warps, and every warp reduces the CS records redundantly.  Records and barriers are
+// double-buffered by round parity: a CTA can write round r+2's record only after round r+1 completed everywhere,
+// i.e. after every peer has consumed round r's.
 template <int NT, int PPT, int CS>
 __global__ void __launch_bounds__(NT)
 fps_cluster_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
                    float *__restrict__ temp, int *__restrict__ idxs, float *__restrict__ new_xyz) {
-    constexpr int NW = NT / 32, NREC = CS * NW;           // records per round: one per warp of the cluster
-    static_assert(NREC <= 256, "at most eight records per lane in the final reduction");
-    __shared__ uint32_t rec[2][5][NREC];                  // [round parity][dist, key, x, y, z][cluster warp]
+    constexpr int NW = NT / 32;
+    static_assert(CS <= 32 && NW <= 32, "one record per lane in the reductions");
+    __shared__ uint32_t wrec[2][5][NW];                   // per-warp records of this CTA [round parity]
+    __shared__ uint32_t crec[2][5][CS];                   // per-CTA records of the cluster (written remotely)
+    __shared__ uint64_t xbar[2];                          // CS arrivals each
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t crank = cluster_ctarank();
     const int b = blockIdx.x / CS;
@@ -213,6 +238,11 @@ fps_cluster_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset
     const int ref_shift = ref_bits ? 32 - ref_bits : 31;
     const bool writer = crank == 0 && tid == 0;
 
+    if (tid == 0) {
+        mbar_init_cl(&xbar[0], CS);
+        mbar_init_cl(&xbar[1], CS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     float x[PPT], y[PPT], z[PPT], t[PPT];
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
@@ -228,11 +258,12 @@ fps_cluster_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset
         out[0] = 0;
         if (oxyz) { oxyz[0] = ox; oxyz[1] = oy; oxyz[2] = oz; }
     }
-    // this warp's record slot in every CTA of the cluster
-    const uint32_t slot_addr = (uint32_t)__cvta_generic_to_shared(&rec[0][0][crank * NW + warp]);
-    cluster_sync_all();                                   // every CTA of the cluster is resident before remote stores
+    const uint32_t crec_addr = (uint32_t)__cvta_generic_to_shared(&crec[0][0][crank]);
+    const uint32_t xbar_addr = (uint32_t)__cvta_generic_to_shared(&xbar[0]);
+    cluster_sync_all();                                   // barriers initialised and every CTA resident before remote traffic
 
     for (int r = 1; r < m; ++r) {
+        const int par = r & 1;
         float tm = -INFINITY;
 #pragma unroll
         for (int j = 0; j < PPT; ++j) {
@@ -253,35 +284,40 @@ fps_cluster_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset
         }
         const unsigned wt = __reduce_max_sync(kFull, tb);
         if (um == wm && tb == wt) {                        // exactly one lane: keys are unique
-            const uint32_t po = slot_addr + (uint32_t)((r & 1) * 5 * NREC) * 4u;
-            const uint32_t w[5] = {wm, wt, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz)};
-#pragma unroll
-            for (int c = 0; c < CS; ++c) {
-                const uint32_t ra = mapa_shared(po, (uint32_t)c);     // the same slot in CTA c of the cluster
-#pragma unroll
-                for (int q = 0; q < 5; ++q) st_cluster_u32(ra + (uint32_t)(q * NREC) * 4u, w[q]);
-            }
+            wrec[par][0][warp] = wm; wrec[par][1][warp] = wt;
+            wrec[par][2][warp] = __float_as_uint(bx); wrec[par][3][warp] = __float_as_uint(by); wrec[par][4][warp] = __float_as_uint(bz);
         }
-        cluster_sync_all();
-        // every warp reduces the NREC records redundantly (lane l: records l, l+32, ...)
-        unsigned qm = 0, qt = 0;
-        int qi = 0;
-#pragma unroll
-        for (int i = 0; i < (NREC + 31) / 32; ++i) {
-            const int e = lane + 32 * i;
-            if (e < NREC) {
-                const unsigned em = rec[r & 1][0][e], et = rec[r & 1][1][e];
-                if (em > qm || (em == qm && et > qt)) { qm = em; qt = et; qi = e; }
+        __syncthreads();
+        if (warp == 0) {
+            // CTA winner among the NW warp records
+            const unsigned qm = lane < NW ? wrec[par][0][lane] : 0u, qt = lane < NW ? wrec[par][1][lane] : 0u;
+            const unsigned cm = __reduce_max_sync(kFull, qm);
+            const unsigned ct = __reduce_max_sync(kFull, qm == cm ? qt : 0u);
+            const int src = __ffs(__ballot_sync(kFull, qm == cm && qt == ct)) - 1;
+            // lane c < CS delivers the record to CTA c and arrives on its barrier (release at cluster scope)
+            if (lane < CS) {
+                const uint32_t ra = mapa_shared(crec_addr + (uint32_t)(par * 5 * CS) * 4u, (uint32_t)lane);
+                st_cluster_u32(ra, cm);
+                st_cluster_u32(ra + (uint32_t)CS * 4u, ct);
+                st_cluster_u32(ra + (uint32_t)(2 * CS) * 4u, wrec[par][2][src]);
+                st_cluster_u32(ra + (uint32_t)(3 * CS) * 4u, wrec[par][3][src]);
+                st_cluster_u32(ra + (uint32_t)(4 * CS) * 4u, wrec[par][4][src]);
+                mbar_remote_arrive_release(mapa_shared(xbar_addr + (uint32_t)par * 8u, (uint32_t)lane));
             }
+            if (lane == 0)
+                // xbar[1] serves rounds 1, 3, 5, ..., xbar[0] rounds 2, 4, 6, ...: the use count of either is (r - 1) / 2
+                while (!mbar_try_wait_acquire_cluster(&xbar[par], (uint32_t)(((r - 1) >> 1) & 1))) {}
+            __syncwarp();
         }
-        const unsigned bm = __reduce_max_sync(kFull, qm);
-        const unsigned bt = __reduce_max_sync(kFull, qm == bm ? qt : 0u);
-        const unsigned who = __ballot_sync(kFull, qm == bm && qt == bt);
-        const int src = __ffs(who) - 1;
-        const int wi = __shfl_sync(kFull, qi, src);
-        ox = __uint_as_float(rec[r & 1][2][wi]);
-        oy = __uint_as_float(rec[r & 1][3][wi]);
-        oz = __uint_as_float(rec[r & 1][4][wi]);
+        __syncthreads();
+        // every warp reduces the CS cluster records redundantly
+        const unsigned em = lane < CS ? crec[par][0][lane] : 0u, et = lane < CS ? crec[par][1][lane] : 0u;
+        const unsigned bm = __reduce_max_sync(kFull, em);
+        const unsigned bt = __reduce_max_sync(kFull, em == bm ? et : 0u);
+        const int wi = __ffs(__ballot_sync(kFull, em == bm && et == bt)) - 1;
+        ox = __uint_as_float(crec[par][2][wi]);
+        oy = __uint_as_float(crec[par][3][wi]);
+        oz = __uint_as_float(crec[par][4][wi]);
         if (writer) {
             out[r] = (int)((~bt) & 0x3fffffu);
             if (oxyz) { oxyz[r * 3 + 0] = ox; oxyz[r * 3 + 1] = oy; oxyz[r * 3 + 2] = oz; }

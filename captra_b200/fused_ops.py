@@ -1,6 +1,7 @@
 """Thin Python fronts for the fused entry points of include/captra_ops.h section 2.
 Point-major tensors in, point-major tensors out; every call is one or two kernel launches."""
 import ctypes
+import os
 
 import torch
 
@@ -14,7 +15,10 @@ def fps_gather(xyz, npoint):
     B, N, _ = xyz.shape
     idx = torch.empty(B, npoint, dtype=_i32, device=xyz.device)
     new_xyz = torch.empty(B, npoint, 3, dtype=_f32, device=xyz.device)
-    temp = torch.full((B, N), 1e10, dtype=_f32, device=xyz.device) if N > 32768 else None   # registers (one CTA or a cluster) below that
+    # registers (one CTA, or a cluster above 8192 points) hold the running distances up to 32768 points; the streaming
+    # kernel beyond that (or with CAPTRA_FPS_CLUSTER=0, an A/B knob) keeps them in a scratch tensor
+    need_temp = N > 32768 or (N > 8192 and os.environ.get("CAPTRA_FPS_CLUSTER") == "0")
+    temp = torch.full((B, N), 1e10, dtype=_f32, device=xyz.device) if need_temp else None
     _lib.call("fps_gather[B=%d,N=%d,M=%d]" % (B, N, npoint), _lib.load().captra_fps_gather, B, N, npoint,
               _lib.ptr(xyz, _f32, "xyz"), temp.data_ptr() if temp is not None else None, idx.data_ptr(), new_xyz.data_ptr(),
               _lib.stream_ptr(xyz.device), device=xyz.device)

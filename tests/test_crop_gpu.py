@@ -41,8 +41,11 @@ def test_device_crop_recurses_when_window_is_empty(cuda):
     depth, mask, c, K = synthetic.depth_scene(seed=9, obj_radius=0.1, obj_depth=0.9, holes=0.0)
     win = data_crop.get_proj_corners(depth.shape, c, 0.05, K)
     depth[win[0, 0]:win[1, 0] + 1, win[0, 1]:win[1, 1] + 1] = 0.0
-    want_pts, want_mask, _ = crop_ref.crop_ball_from_depth_image(depth, mask, c, 0.05, K, 256)
-    pts, obj_mask = data_crop.crop_ball_from_depth_image(torch.from_numpy(depth).to(cuda), torch.from_numpy(mask).to(cuda), c, 0.05,
-                                                        cam_intrinsics=K, num_points=256)
+    perm = np.random.default_rng(0).permutation(1 << 16)          # more than any crop here; only its head is used
+    want_pts, want_mask, _ = crop_ref.crop_ball_from_depth_image(depth, mask, c, 0.05, K, 256, perm=perm[perm < 2340])
+    pts, obj_mask, info = data_crop.crop_ball_from_depth_image(torch.from_numpy(depth).to(cuda), torch.from_numpy(mask).to(cuda), c, 0.05,
+                                                              cam_intrinsics=K, num_points=256, perm=torch.from_numpy(perm[perm < 2340]).to(cuda),
+                                                              return_info=True)
+    assert info["n"] == 2340
     np.testing.assert_allclose(pts.cpu().numpy(), want_pts, rtol=1e-12, atol=1e-15)
     np.testing.assert_array_equal(obj_mask.cpu().numpy(), want_mask)
