@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "det_accum.cuh"
 
 namespace captra {
 
@@ -104,6 +105,21 @@ scatter_add_rows_kernel(int c, int n, int64_t L, const float *__restrict__ grad_
         atomicAdd(grad_points + ((size_t)b * c + ci) * n + id, __ldg(grad_out + ((size_t)b * c + ci) * L + j));
 }
 
+// deterministic variant (det_accum.cuh): same traversal, 64-bit fixed-point integer atomics
+__global__ void __launch_bounds__(GG_THREADS)
+scatter_add_rows_det_kernel(int c, int n, int64_t L, const float *__restrict__ grad_out,
+                            const int *__restrict__ idx, long long *__restrict__ acc, DetScale sc) {
+    const int b = blockIdx.z;
+    const int cblk = blockIdx.y * GG_CH_BLOCK;
+    const int cend = min(c, cblk + GG_CH_BLOCK);
+    const int64_t j = (int64_t)blockIdx.x * GG_THREADS + threadIdx.x;
+    if (j >= L) return;
+    const int e = sc.exponent();
+    const int id = __ldg(idx + (size_t)b * L + j);
+    for (int ci = cblk; ci < cend; ++ci)
+        det_add(acc + ((size_t)b * c + ci) * n + id, __ldg(grad_out + ((size_t)b * c + ci) * L + j), e);
+}
+
 static int launch_gather(const char *name, int b, int c, int n, int64_t L, const float *points,
                          const int *idx, float *out, cudaStream_t stream) {
     CAPTRA_REQUIRE(b >= 0 && c >= 0 && n >= 0 && L >= 0, "%s: negative size", name);
@@ -168,6 +184,21 @@ static int launch_scatter(const char *name, int b, int c, int n, int64_t L, cons
     CAPTRA_REQUIRE(grad_out && idx && grad_points, "%s: null pointer", name);
     CAPTRA_REQUIRE(b <= 65535 && ceil_div(c, GG_CH_BLOCK) <= 65535, "%s: grid limit", name);
     dim3 grid((unsigned)ceil_div<int64_t>(L, GG_THREADS), ceil_div(c, GG_CH_BLOCK), b);
+    if (det_enabled()) {
+        long long *acc = nullptr;
+        unsigned *maxbits = nullptr;
+        int rc = det_begin(grad_out, (int64_t)b * c * L, (int64_t)b * c * n, &acc, &maxbits, stream);
+        if (rc) return rc;
+        scatter_add_rows_det_kernel<<<grid, GG_THREADS, 0, stream>>>(c, n, L, grad_out, idx, acc, DetScale{maxbits, 0});
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaFreeAsync(acc, stream);
+            set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e));
+            return CAPTRA_ERR_CUDA;
+        }
+        count_launch();
+        return det_finish(acc, maxbits, 0, (int64_t)b * c * n, grad_points, stream);
+    }
     scatter_add_rows_kernel<<<grid, GG_THREADS, 0, stream>>>(c, n, L, grad_out, idx, grad_points);
     CAPTRA_CHECK_LAUNCH(name);
     return CAPTRA_OK;

@@ -8,6 +8,7 @@
 // The reference compares in double against 1e40 sentinels (interpolate_gpu.cu:102-120); a
 // float +inf sentinel orders every float d identically and converts to the same float output.
 #include "common.cuh"
+#include "det_accum.cuh"
 
 #include <math.h>
 
@@ -178,6 +179,30 @@ three_interpolate_grad_kernel(int c, int n, int m, const float *__restrict__ gra
     }
 }
 
+// deterministic variant (det_accum.cuh): the fp32 products g * w are formed as in the reference, accumulated in 64-bit
+// fixed point; max|grad_out| bounds the products of convex weights, and 8 bits of head-room cover callers whose weights
+// are not (|w| <= 256; the resolution is still 2^-33 max|grad_out|, far below fp32's 2^-24)
+__global__ void __launch_bounds__(NN_THREADS)
+three_interpolate_grad_det_kernel(int c, int n, int m, const float *__restrict__ grad_out,
+                                  const int *__restrict__ idx, const float *__restrict__ weight,
+                                  long long *__restrict__ acc, DetScale sc) {
+    const int b = blockIdx.z;
+    const int pt = blockIdx.x * NN_THREADS + threadIdx.x;
+    if (pt >= n) return;
+    const int e = sc.exponent();
+    const size_t o = ((size_t)b * n + pt) * 3;
+    const int i0 = __ldg(idx + o), i1 = __ldg(idx + o + 1), i2 = __ldg(idx + o + 2);
+    const float w0 = __ldg(weight + o), w1 = __ldg(weight + o + 1), w2 = __ldg(weight + o + 2);
+    const int cblk = blockIdx.y * TI_CH_BLOCK, cend = min(c, cblk + TI_CH_BLOCK);
+    for (int ci = cblk; ci < cend; ++ci) {
+        const float g = __ldg(grad_out + ((size_t)b * c + ci) * n + pt);
+        long long *dst = acc + ((size_t)b * c + ci) * m;
+        det_add(dst + i0, __fmul_rn(g, w0), e);
+        det_add(dst + i1, __fmul_rn(g, w1), e);
+        det_add(dst + i2, __fmul_rn(g, w2), e);
+    }
+}
+
 // knn (interpolate_gpu.cu:9-57): sorted insertion list of k <= 200 candidates per query.
 // The list lives in shared memory (k floats + k ints per thread would spill 2.4 kB/thread in
 // the reference); strict '<' keeps the earlier index on ties exactly like the reference.
@@ -270,6 +295,22 @@ extern "C" int three_interpolate_grad_kernel_launcher_fast(int b, int c, int n, 
     CAPTRA_REQUIRE(grad_out && idx && weight && grad_points, "three_interpolate_grad: null pointer");
     CAPTRA_REQUIRE(b <= 65535 && ceil_div(c, TI_CH_BLOCK) <= 65535, "three_interpolate_grad: grid limit");
     dim3 grid(ceil_div(n, NN_THREADS), ceil_div(c, TI_CH_BLOCK), b);
+    if (det_enabled()) {
+        cudaStream_t s = as_stream(stream);
+        long long *acc = nullptr;
+        unsigned *maxbits = nullptr;
+        int rc = det_begin(grad_out, (int64_t)b * c * n, (int64_t)b * c * m, &acc, &maxbits, s);
+        if (rc) return rc;
+        three_interpolate_grad_det_kernel<<<grid, NN_THREADS, 0, s>>>(c, n, m, grad_out, idx, weight, acc, DetScale{maxbits, 8});
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaFreeAsync(acc, s);
+            set_error("three_interpolate_grad: CUDA launch failed: %s", cudaGetErrorString(e));
+            return CAPTRA_ERR_CUDA;
+        }
+        count_launch();
+        return det_finish(acc, maxbits, 8, (int64_t)b * c * m, grad_points, s);
+    }
     three_interpolate_grad_kernel<<<grid, NN_THREADS, 0, as_stream(stream)>>>(c, n, m, grad_out, idx, weight, grad_points);
     CAPTRA_CHECK_LAUNCH("three_interpolate_grad");
     return CAPTRA_OK;

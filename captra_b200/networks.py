@@ -23,6 +23,7 @@ from .backbones import PointNet2Msg
 from .mlp import PackedMLP, fold_conv_bn, group_norm_affine, group_norm_finalize
 from .pointnet_utils import _FusedCache, _needs_autograd
 from .pose_utils.pose_fit import part_fit_st_no_ransac
+from .pose_utils.procrustes import rot_around_yaxis_to_3d, scale_pts_mask, transform_pts_2d_mask, translate_pts_mask
 
 
 # ---- pose_utils/rotations.py:300-387, part_dof_utils.py:124-141 (elementwise glue) ---------------
@@ -203,9 +204,51 @@ class CoordNet(nn.Module):
             self._cache = _FusedCache()
         return self._cache.get(self, build)
 
+    def _pose_branch(self, input, seg, nocs, test):
+        """networks.py:54-108: the training-time scale / translation fit from the predicted NOCS with the ground-truth
+        rotation -- differentiable through scale_pts_mask / translate_pts_mask, 2-D rotation detached (as in the
+        reference); torch ops on the device, the 2x2 SVD on the device kernel instead of the CPU."""
+        P = self.num_parts
+        pred_labels = torch.argmax(seg, dim=-2)
+        labels = pred_labels if test else input['labels']
+        rotation = input['gt_part']['rotation']
+        final_pose = {'rotation': rotation}
+        pred_npcs = nocs.reshape(len(nocs), P, 3, -1)
+        cam_points = (input['points'] + input['points_mean']).unsqueeze(1).repeat(1, P, 1, 1)
+        eye = torch.cat([torch.eye(P), torch.zeros(2, P)], dim=0).to(pred_npcs.device)
+        mask = eye[labels, ].transpose(-1, -2)                       # [B, N, P] -> [B, P, N]
+        valid_mask = (mask.sum(dim=-1) > 0).float()
+        init_part = input['init_part']
+        if self.sym:
+            canon_cam = torch.matmul(rotation.transpose(-1, -2), cam_points)
+            src_2d = pred_npcs[..., [0, 2], :].transpose(-1, -2)
+            tgt_2d = canon_cam[..., [0, 2], :].transpose(-1, -2)
+            rot_2d, _ = transform_pts_2d_mask(src_2d, tgt_2d, mask.unsqueeze(-1))
+            rotated_npcs = torch.matmul(rotation, torch.matmul(rot_around_yaxis_to_3d(rot_2d), pred_npcs))
+        else:
+            rotated_npcs = torch.matmul(rotation, pred_npcs)
+        scale_mask = mask.unsqueeze(-2)                              # [B, P, 1, N]
+
+        def center(source, m):
+            c = torch.sum(source * m, dim=-1, keepdim=True) / torch.clamp(torch.sum(m, dim=-1, keepdim=True), min=1.0)
+            return (source - c.detach()) * m
+
+        scale = scale_pts_mask(center(rotated_npcs, scale_mask), center(cam_points, scale_mask), scale_mask)
+        scale = valid_mask * scale + (1.0 - valid_mask) * init_part['scale']
+        bad = torch.logical_or(torch.isnan(scale), torch.isinf(scale)).float()
+        final_pose['scale'] = (1.0 - bad) * scale + bad * init_part['scale']
+        used = final_pose['scale'] if test else input['gt_part']['scale']
+        scaled_npcs = used.unsqueeze(-1).unsqueeze(-1) * rotated_npcs
+        trans = translate_pts_mask(scaled_npcs, cam_points, mask.unsqueeze(-1))
+        v = valid_mask.unsqueeze(-1).unsqueeze(-1)
+        trans = v * trans + (1.0 - v) * init_part['translation']
+        s = trans.sum((-1, -2))
+        bad = torch.logical_or(torch.isnan(s), torch.isinf(s)).float().unsqueeze(-1).unsqueeze(-1)
+        final_pose['translation'] = (1.0 - bad) * trans + bad * init_part['translation']
+        return final_pose
+
     def forward(self, input, test=False):
-        assert 'gt_part' not in input, "training-time pose branch (networks.py:54-108) is not mirrored"
-        if not _needs_autograd(self, input['points']):
+        if 'gt_part' not in input and not _needs_autograd(self, input['points']):
             pose = input['canon_pose']
             geom = input.get('geom')
             xyz_pm, cam, dup = frame_ops.canonicalize(input['points'], input['points_mean'], pose['rotation'],
@@ -223,7 +266,10 @@ class CoordNet(nn.Module):
         feat = self.backbone(cam)
         seg = F.softmax(self.seg_head(feat), dim=1)
         nocs = self.nocs_head(feat) - 0.5
-        return {'seg': seg, 'nocs': nocs, 'points': cam}
+        pred = {'seg': seg, 'nocs': nocs, 'points': cam}
+        if 'gt_part' in input:                 # compute s, t from the predicted NOCS (training / evaluation of CoordNet alone)
+            pred['part'] = self._pose_branch(input, seg, nocs, test)
+        return pred
 
 
 class RotationRegressionBackbone(nn.Module):

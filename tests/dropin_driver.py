@@ -97,4 +97,40 @@ for category in ("bottle", "laptop"):
         "procrustes_module": sys.modules["pose_utils.procrustes"].__name__ if "pose_utils.procrustes" in sys.modules else None,
     }
 out["frame"] = res
+
+# ---- (3) training drop-in: the reference's CoordNet in TRAINING mode (BatchNorm batch statistics, autograd through the
+# drop-in ops and the differentiable scale / translation fit, networks.py:54-108) vs this package's mirror in training mode
+from captra_b200 import networks as ON   # noqa: E402
+tr = {}
+for category in ("bottle", "laptop"):
+    cfg = track.make_cfg(category, device=str(dev))
+    P = cfg["num_parts"]
+    ref_net = track.init_weights(RN.CoordNet(cfg), 5).to(dev).train()
+    our_net = track.init_weights(ON.CoordNet(cfg), 5).to(dev).train()
+    b = track.synthetic_track_batch(2, category, n=1024, seed=3)
+    gen = torch.Generator().manual_seed(1)
+    inp = {"points": torch.from_numpy(b["points"]).to(dev), "points_mean": torch.from_numpy(b["points_mean"]).to(dev),
+           "labels": torch.randint(0, P + cfg["obj"]["extra_dims"], (2, 1024), generator=gen).to(dev),
+           "gt_part": {k: torch.from_numpy(np.asarray(v, dtype=np.float32)).to(dev) for k, v in b["gt"].items()},
+           "init_part": {k: torch.from_numpy(v).to(dev) for k, v in b["pose"].items()}}
+    inp["canon_pose"] = {k: inp["init_part"][k][:, 0] for k in ("rotation", "translation", "scale")}
+    grads = []
+    outs = []
+    for net in (ref_net, our_net):
+        with torch.device(dev):
+            pred = net(dict(inp))
+        loss = (pred["nocs"] ** 2).mean() + pred["seg"][:, 0].mean() + pred["part"]["scale"].sum() + pred["part"]["translation"].abs().sum()
+        net.zero_grad()
+        loss.backward()
+        grads.append({k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None})
+        outs.append({"loss": float(loss), "scale": pred["part"]["scale"].detach(), "translation": pred["part"]["translation"].detach(),
+                     "nocs": pred["nocs"].detach()})
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 50
+    rel = max(float((grads[0][k] - grads[1][k]).abs().max() / (grads[0][k].abs().max() + 1e-12)) for k in grads[0])
+    tr[category] = {"loss_ref": outs[0]["loss"], "loss_ours": outs[1]["loss"], "params_with_grad": len(grads[0]),
+                    "nocs_max_abs": float((outs[0]["nocs"] - outs[1]["nocs"]).abs().max()),
+                    "scale_max_abs": float((outs[0]["scale"] - outs[1]["scale"]).abs().max()),
+                    "translation_max_abs": float((outs[0]["translation"] - outs[1]["translation"]).abs().max()),
+                    "grad_max_rel": rel}
+out["train"] = tr
 print(json.dumps(out))

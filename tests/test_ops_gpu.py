@@ -283,3 +283,44 @@ def test_fps_cluster_path(n, m, kind, oracle, cuda):
     want = oracle.furthest_point_sample(pts, m)
     assert np.array_equal(idx.cpu().numpy(), want)
     assert np.array_equal(new_xyz.cpu().numpy(), np.take_along_axis(pts, want.astype(np.int64)[..., None], 1))
+
+
+def test_backward_ops_are_deterministic_and_correctly_rounded(cuda):
+    """The three training-only adjoints accumulate in 64-bit fixed point (csrc/det_accum.cuh): bit-identical from run to
+    run whatever the atomics' interleaving (the reference's fp32 atomicAdd is not: group_points_gpu.cu:8-25,
+    sampling_gpu.cu:46-63, interpolate_gpu.cu:192-214), and equal to the exactly summed gradient rounded to fp32."""
+    from captra_b200 import pointnet2_cuda as P
+    gen = torch.Generator().manual_seed(0)
+    B, C, N, M, K, n = 2, 32, 64, 256, 64, 5000                       # few destinations, thousands of colliding contributions each
+    idx = torch.randint(0, N, (B, M, K), generator=gen, dtype=torch.int32).to(cuda)
+    g = (torch.randn(B, C, M, K, generator=gen) * torch.logspace(-6, 2, C).view(1, C, 1, 1)).to(cuda)   # 8 decades of magnitudes
+    runs = []
+    for _ in range(3):
+        out = torch.zeros(B, C, N, device=cuda)
+        P.group_points_grad_wrapper(B, C, N, M, K, g, idx, out)
+        runs.append(out)
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    exact = torch.zeros(B, C, N, dtype=torch.float64, device=cuda)
+    exact.scatter_add_(2, idx.view(B, 1, M * K).expand(-1, C, -1).long(), g.double().view(B, C, M * K))
+    # the fixed-point grid is 2^-41 of the call's max|g| per contribution
+    tol = float(g.abs().max()) * M * K * 2.0 ** -41
+    assert float((runs[0].double() - exact).abs().max()) <= tol + float(exact.abs().max()) * 2.0 ** -24
+    idx3 = torch.randint(0, N, (B, n, 3), generator=gen, dtype=torch.int32).to(cuda)
+    w = torch.rand(B, n, 3, generator=gen).to(cuda)
+    g3 = torch.randn(B, C, n, generator=gen).to(cuda)
+    runs = []
+    for _ in range(3):
+        out = torch.zeros(B, C, N, device=cuda)
+        P.three_interpolate_grad_wrapper(B, C, n, N, g3, idx3, w, out)
+        runs.append(out)
+    assert torch.equal(runs[0], runs[1]) and torch.equal(runs[0], runs[2])
+    exact = torch.zeros(B, C, N, dtype=torch.float64, device=cuda)
+    for j in range(3):
+        exact.scatter_add_(2, idx3[..., j].view(B, 1, n).expand(-1, C, -1).long(), (g3 * w[..., j].view(B, 1, n)).double())
+    assert float((runs[0].double() - exact).abs().max()) <= 1e-5 * float(exact.abs().max())
+    sidx = torch.randint(0, N, (B, M), generator=gen, dtype=torch.int32).to(cuda)
+    g2 = torch.randn(B, C, M, generator=gen).to(cuda)
+    a, b = torch.zeros(B, C, N, device=cuda), torch.zeros(B, C, N, device=cuda)
+    P.gather_points_grad_wrapper(B, C, N, M, g2, sidx, a)
+    P.gather_points_grad_wrapper(B, C, N, M, g2, sidx, b)
+    assert torch.equal(a, b)
