@@ -286,11 +286,16 @@ class RotationRegressionBackbone(nn.Module):
         """Fused inference path: xyz_pm [B*P,N,3] (copy p canonicalised by part p), labels [B,N], rot_prev [B,P,3,3]
         -> rotation [B,P,3,3] = rot_prev . dR: encoder, head p on copy p (networks.py:200-203 keeps that diagonal only),
         then ONE launch for per-point 6-D / 3-D -> matrix, masked mean, default, Gram-Schmidt and composition."""
+        raws = self.forward_heads(xyz_pm, batch_size, geom=geom)
+        return frame_ops.rot_head_post(raws, labels, rot_prev, self.sym, want_rtvec=want_rtvec)
+
+    def forward_heads(self, xyz_pm, batch_size, geom=None):
+        """Encoder + head p on copy p -> P raw per-point outputs [B,N,D] (point-major): everything of the rotation
+        network that does NOT depend on the CoordNet's labels, so it can run on a second stream beside the CoordNet."""
         P = self.num_parts
         feat_pm = self.encoder.forward_pm(None, geom=geom, xyz_pm=xyz_pm)      # [B*P, N, C]
         feat_pm = feat_pm.reshape(batch_size, P, feat_pm.shape[1], feat_pm.shape[2])
-        raws = [self.pose_pred.rtvec_head[p].forward_pm(feat_pm[:, p] if P == 1 else feat_pm[:, p].contiguous()) for p in range(P)]
-        return frame_ops.rot_head_post(raws, labels, rot_prev, self.sym, want_rtvec=want_rtvec)
+        return [self.pose_pred.rtvec_head[p].forward_pm(feat_pm[:, p] if P == 1 else feat_pm[:, p].contiguous()) for p in range(P)]
 
     def forward_diag(self, cam, labels, batch_size):
         """Autograd / training-mode path in torch ops, as the reference composes it: cam [B*P,3,N] (copy p
@@ -338,12 +343,17 @@ class PartCanonNet(nn.Module):
         labels = input['pred_labels']               # [B,N]
         if not _needs_autograd(self, cam):
             shared = input.get('geom') if P == 1 and 'canon_pose' not in input else None
-            if shared is not None and 'xyz_pm' in shared:
+            if 'rot_raws' in input:
+                xyz_pm = None
+            elif shared is not None and 'xyz_pm' in shared:
                 xyz_pm = shared['xyz_pm']            # rigid object: CoordNet canonicalised by the same pose
             else:
                 xyz_pm = frame_ops.canonicalize(cam, points_mean, canon_pose['rotation'], canon_pose['translation'],
                                                 canon_pose['scale'], parts=P)[0]
-            rotation = self.regress_net.forward_rotation(xyz_pm, labels, part_pose['rotation'], B, geom=shared)
+            if 'rot_raws' in input:      # the tracker already ran the label-independent part on its second stream
+                rotation = frame_ops.rot_head_post(input['rot_raws'], labels, part_pose['rotation'], self.sym)
+            else:
+                rotation = self.regress_net.forward_rotation(xyz_pm, labels, part_pose['rotation'], B, geom=shared)
             pred_npcs = input['pred_nocs'].reshape(B, P, 3, -1)
             scale, translation, _ = frame_ops.part_fit_track(labels, pred_npcs.contiguous(), cam, points_mean, rotation, self.sym,
                                                              part_pose['scale'], part_pose['translation'])

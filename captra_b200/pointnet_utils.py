@@ -112,6 +112,38 @@ def _needs_autograd(module, *tensors):
     return any(t is not None and t.requires_grad for t in tensors) or any(p.requires_grad for p in module.parameters())
 
 
+class SharedGeom(dict):
+    """Coordinate-only results (FPS picks, ball-query lists, 3-NN indices / weights, the canonicalised cloud) shared by
+    two networks that run on DIFFERENT CUDA streams: storing an item records an event on the producing stream, reading it
+    from another stream makes that stream wait for the event.  The producer's launches must be enqueued (host side)
+    before the consumer asks; on the device the two chains then overlap wherever the data dependencies allow."""
+
+    def __init__(self):
+        super().__init__()
+        self._ev = {}
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        ev = torch.cuda.Event()
+        st = torch.cuda.current_stream()
+        ev.record(st)
+        self._ev[key] = (ev, st)
+
+    def __getitem__(self, key):
+        value = super().__getitem__(key)
+        rec = self._ev.get(key)
+        if rec is not None:
+            cur = torch.cuda.current_stream()
+            if cur != rec[1]:
+                cur.wait_event(rec[0])
+        return value
+
+    def setdefault(self, key, default=None):
+        if key not in self:
+            super().__setitem__(key, SharedGeom() if isinstance(default, dict) and not default else default)
+        return super().__getitem__(key)
+
+
 def _pm(t):
     """[B,C,N] -> point-major contiguous [B,N,C]."""
     return t.transpose(1, 2).contiguous()

@@ -4,6 +4,8 @@ the B200 kernels, plus the synthetic workloads of BASELINE.json used by bench.py
 One "frame" = CoordNet forward on B clouds + argmax labels + PartCanonNet forward on B*P
 canonicalised clouds + fused pose fit -> the new 9-DoF part poses for B trajectories.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -151,6 +153,37 @@ class Tracker(torch.nn.Module):
         self.net = init_weights(PartCanonNet(cfg), seed + 1)
         self.num_parts = cfg["num_parts"]
         self.root = [p for p in range(self.num_parts) if cfg["obj_tree"][p] == -1][0]
+        self._side = {}
+
+    # The rotation network's encoder and heads do not depend on the CoordNet's output (only the final masked mean needs
+    # its labels), and each chain has phases that leave most of the GPU idle (FPS: one CTA per cloud; the group-all /
+    # fp3 layers: 32 tiles for 148 SMs).  CAPTRA_TWO_STREAM=0 runs the two networks back to back (A/B knob).
+    TWO_STREAM = os.environ.get("CAPTRA_TWO_STREAM", "1") != "0"
+
+    def _side_stream(self, device):
+        if device not in self._side:
+            self._side[device] = torch.cuda.Stream(device)
+        return self._side[device]
+
+    def _step_two_stream(self, points, points_mean, last_pose, canon):
+        from . import frame_ops
+        from .pointnet_utils import SharedGeom
+        P, B = self.num_parts, points.shape[0]
+        main = torch.cuda.current_stream(points.device)
+        side = self._side_stream(points.device)
+        geom = SharedGeom() if P == 1 else None
+        side.wait_stream(main)                      # the frame's inputs
+        # CoordNet on the current stream; every coordinate-only result it produces carries an event
+        pred = self.npcs_net({"points": points, "points_mean": points_mean, "canon_pose": canon, "geom": geom})
+        with torch.cuda.stream(side):
+            if P == 1:
+                xyz_pm = geom["xyz_pm"]             # waits (on the device) for the CoordNet's canonicalisation only
+            else:
+                flat = {k: last_pose[k].reshape((-1,) + last_pose[k].shape[2:]) for k in ("rotation", "translation", "scale")}
+                xyz_pm = frame_ops.canonicalize(points, points_mean, flat["rotation"], flat["translation"], flat["scale"], parts=P)[0]
+            raws = self.net.regress_net.forward_heads(xyz_pm, B, geom=geom)
+        main.wait_stream(side)
+        return pred, raws
 
     @torch.no_grad()
     def step(self, points, points_mean, last_pose, want_pred=False):
@@ -161,13 +194,19 @@ class Tracker(torch.nn.Module):
         # With one rigid part both networks see the cloud canonicalised by the same pose
         # (networks.py:38-41 vs :184-187), so FPS picks, ball-query lists and 3-NN weights -- functions
         # of the coordinates only -- are computed once and shared (bit-identical results).
-        geom = {} if self.num_parts == 1 else None
-        pred = self.npcs_net({"points": points, "points_mean": points_mean, "canon_pose": canon, "geom": geom})
+        extra = {}
+        fused = points.is_cuda and not self.training
+        if fused and self.TWO_STREAM:
+            pred, extra["rot_raws"] = self._step_two_stream(points, points_mean, last_pose, canon)
+            geom = None
+        else:
+            geom = {} if self.num_parts == 1 else None
+            pred = self.npcs_net({"points": points, "points_mean": points_mean, "canon_pose": canon, "geom": geom})
         B = points.shape[0]
         pred_npcs = pred["nocs"].reshape(B, self.num_parts, 3, -1)
         pred_labels = pred["labels"] if "labels" in pred else torch.max(pred["seg"], dim=-2)[1]
-        out = self.net({"points": points, "points_mean": points_mean, "state": {"part": last_pose},
-                        "pred_labels": pred_labels, "pred_nocs": pred_npcs, "geom": geom}, test_mode=True)
+        out = self.net(dict({"points": points, "points_mean": points_mean, "state": {"part": last_pose},
+                             "pred_labels": pred_labels, "pred_nocs": pred_npcs, "geom": geom}, **extra), test_mode=True)
         if want_pred:
             return out["part"], {"seg": pred["seg"], "nocs": pred["nocs"], "labels": pred_labels, "points": pred["points"]}
         return out["part"]

@@ -1,4 +1,4 @@
-"""CPU: the reference arm of bench.py (`--impl reference`: the CPU port of the frame step timed on the host cores)
+"""CPU: the reference arm of bench.py (`--impl reference`: the reference's CPU implementation of the frame step timed on the host cores)
 prints exactly one JSON line on stdout with the keys the driver reads, and needs no GPU."""
 import json
 import os
@@ -18,7 +18,11 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("tracking frames/sec") and d["value"] > 0
     assert d["config"]["name"] == "cfg2" and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference": the reference's own torch CPU path from oracle/_ref/pyref (built when /root/reference is present);
+    # "port": oracle/frame_ref when that copy is absent
+    want_kind = "reference" if os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "pyref")) else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["frames_per_s_1thread"] > 0 and d["cpu_baseline"]["cpu_model"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
