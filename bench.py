@@ -724,6 +724,10 @@ def main():
         pk = peaks()
         _lib.PROFILE = []
         nprof = 3
+        # per-kernel times are taken with the two networks back to back on one stream (concurrent kernels would
+        # inflate each other's event-to-event time); the timed regions above ran the real two-stream frame
+        for t in (list(trk.trackers.values()) if hasattr(trk, "trackers") else [trk]):
+            t.TWO_STREAM = False
         for i in range(nprof):          # rank 0 only: no collective in here
             flush.zero_()
             r = resident[i % nb]
@@ -807,6 +811,7 @@ def main():
                        l2="flushed between steps (256 MiB memset outside the per-step CUDA-event pairs)",
                        mlp_impl={0: "fp32 CUDA cores", 1: "tcgen05 3xTF32", 2: "tcgen05 fp16x3 (fp32 accumulate, overflow-checked)"}[mlp.DEFAULT_IMPL],
                        launch=graph_note, f16_overflow=overflow,
+                       streams="2 (RotationNet encoder + heads beside the CoordNet)" if track.Tracker.TWO_STREAM else "1",
                        collective="one nccl all_reduce of the accumulated eval sums [%d x %d floats] after the last timed frame" % (len(plan), 5 * P + 5) if world > 1 else "none"),
         "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps},

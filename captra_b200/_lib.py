@@ -99,7 +99,11 @@ PROFILE = None
 
 
 def call(tag, fn, *args, device=None):
-    """Invoke a C-ABI entry point, raise on a non-zero status, optionally time it."""
+    """Invoke a C-ABI entry point, raise on a non-zero status, optionally time it.  The launch goes to `device`
+    (the tensors' device), not to whatever device happens to be current."""
+    if device is not None and device.index is not None and device.index != torch.cuda.current_device():
+        with torch.cuda.device(device):
+            return call(tag, fn, *args, device=None)
     if PROFILE is None:
         status = fn(*args)
     else:

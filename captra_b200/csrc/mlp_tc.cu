@@ -1135,7 +1135,15 @@ static TcLayout tc_layout_v(const captra_mlp_desc &d, bool f16, bool small) {
     L.nstages = (!small && fixed + 4 * per_stage <= budget) ? 4 : 2;
     L.smem_bytes = fixed + (size_t)L.nstages * per_stage;
     if (L.smem_bytes > budget) L.supported = false;
-    if (small && (d.nlayers < 2 || npmax > 128)) L.supported = false;
+    // SMALL keeps two CTAs on an SM, so a CTA owns 256 TMEM columns: fused chains ping-pong between two regions
+    // (layers <= 128 columns); a SINGLE layer needs one region and may be up to 256 columns wide (its 512-wide
+    // variants split over grid.y as in the LARGE shape).  Single-layer launches -- the RotationRegressor heads, sa3,
+    // fp3 -- are latency-bound (ncu: tensor pipe 30 %, issue slots 39 %, 28 % of the warps active): a tile's
+    // load -> convert -> MMA -> epilogue chain is serial inside a CTA, so two half-size CTAs per SM overlap one
+    // tile's epilogue and global loads with the other's MMAs.  CAPTRA_TC_SMALL_WIDE=0 restores one LARGE CTA per SM.
+    static const bool small_wide = [] { const char *e = getenv("CAPTRA_TC_SMALL_WIDE"); return !e || atoi(e) != 0; }();
+    if (small && d.nlayers >= 2 && npmax > 128) L.supported = false;
+    if (small && d.nlayers < 2 && !small_wide) L.supported = false;
     return L;
 }
 
@@ -1289,6 +1297,7 @@ static int tc_point_mlp_ex(int64_t rows, const float *segA, int64_t ldA, int ca,
     a.in_scale = in_scale; a.in_shift = in_shift; a.rows_per_cloud = rows_per_cloud;
     CAPTRA_REQUIRE(stats == nullptr || group == 0, "point_mlp: output statistics need row output (group 0)");
     a.stats = stats;
+    if (a.small && group == 0) smem -= 4096 + 8192;      // dense rows never touch the grouped-max buffer or the SA metadata ring (both sit at the end)
     if (in_scale) {
         // a tile must not straddle two clouds: the kernel stages one cloud's scale/shift rows per tile
         CAPTRA_REQUIRE(rows_per_cloud % TC_ROWS == 0, "point_mlp_affine: rows_per_cloud must be a multiple of %d (got %d)", TC_ROWS, rows_per_cloud);

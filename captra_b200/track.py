@@ -275,10 +275,15 @@ class GraphedStep:
     Inputs are copied into the graph's static buffers; the returned pose tensors are the graph's
     static outputs (clone them to keep a frame's result across calls)."""
 
-    def __init__(self, tracker, points, points_mean, pose, warmup=2, gt=None):
+    def __init__(self, tracker, points, points_mean, pose, warmup=2, gt=None, check_every=0):
         """gt (optional part-pose dict): the graph then also evaluates tracker.eval_sums(gt, new pose) -- the
-        end-of-frame loss / metric reduction -- into self.sums (static), with no extra host launches."""
-        from . import _lib
+        end-of-frame loss / metric reduction -- into self.sums (static), with no extra host launches.
+        check_every = k > 0: every k-th replay synchronises and reads the fp16x3 saturation flag (mlp.f16_overflowed);
+        a saturated operand means the result is not fp32-accurate and raises (re-run with CAPTRA_MLP_IMPL=1).  The
+        flag is always checked once here, after the warm-up frames."""
+        from . import _lib, mlp
+        self.check_every, self._replays = int(check_every), 0
+        mlp.f16_overflowed(reset=True) if mlp.DEFAULT_IMPL == 2 else None
         self.inp = {"points": points.clone(), "points_mean": points_mean.clone(),
                     "pose": {k: v.clone() for k, v in pose.items()}}
         self.gt = {k: v.clone().float() for k, v in gt.items()} if gt is not None else None
@@ -293,6 +298,7 @@ class GraphedStep:
                 tracker.step(self.inp["points"], self.inp["points_mean"], self.inp["pose"])
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._check_overflow()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
@@ -301,7 +307,18 @@ class GraphedStep:
                 self.sums = tracker.eval_sums(self.gt, self.out, out=self.sums, accumulate=True)
         self.launches_per_replay = _lib.launch_count() - n0     # this library's kernels inside the graph
 
+    @staticmethod
+    def _check_overflow():
+        from . import _lib, mlp
+        if mlp.DEFAULT_IMPL == 2 and mlp.f16_overflowed(reset=True):
+            raise _lib.CaptraError("an fp16x3 operand saturated (|activation| >= 65504): poses are not fp32-accurate for this "
+                                   "model / input; run with CAPTRA_MLP_IMPL=1 (3xTF32, full exponent range)")
+
     def __call__(self, points, points_mean, pose, gt=None):
+        self._replays += 1
+        if self.check_every and self._replays % self.check_every == 0:
+            torch.cuda.synchronize()
+            self._check_overflow()
         if gt is not None:
             for k, v in self.gt.items():
                 v.copy_(gt[k], non_blocking=True)

@@ -116,7 +116,7 @@ for category in ("bottle", "laptop"):
     inp["canon_pose"] = {k: inp["init_part"][k][:, 0] for k in ("rotation", "translation", "scale")}
     grads = []
     outs = []
-    for net in (ref_net, our_net):
+    for net in (ref_net, our_net, ref_net):      # the reference twice: its own run-to-run spread (cuDNN algorithm choice, atomics)
         with torch.device(dev):
             pred = net(dict(inp))
         loss = (pred["nocs"] ** 2).mean() + pred["seg"][:, 0].mean() + pred["part"]["scale"].sum() + pred["part"]["translation"].abs().sum()
@@ -130,10 +130,12 @@ for category in ("bottle", "laptop"):
     # zero gradient (pure rounding noise on both sides), so a per-tensor ratio would be meaningless there
     gmax = max(float(g.abs().max()) for g in grads[0].values())
     rel = max(float((grads[0][k] - grads[1][k]).abs().max()) for k in grads[0]) / gmax
+    self_rel = max(float((grads[0][k] - grads[2][k]).abs().max()) for k in grads[0]) / gmax
     tr[category] = {"loss_ref": outs[0]["loss"], "loss_ours": outs[1]["loss"], "params_with_grad": len(grads[0]),
                     "nocs_max_abs": float((outs[0]["nocs"] - outs[1]["nocs"]).abs().max()),
                     "scale_max_abs": float((outs[0]["scale"] - outs[1]["scale"]).abs().max()),
                     "translation_max_abs": float((outs[0]["translation"] - outs[1]["translation"]).abs().max()),
-                    "grad_max_rel": rel}
+                    "grad_max_rel": rel, "grad_ref_vs_ref_rel": self_rel,
+                    "nocs_ref_vs_ref_max_abs": float((outs[0]["nocs"] - outs[2]["nocs"]).abs().max())}
 out["train"] = tr
 print(json.dumps(out))
