@@ -142,6 +142,10 @@ def algorithmic(tag):
         N, S = int(kv["N"]), int(kv["S"])
         Ks = [int(k) for k in kv["K"].split("/")]
         return 12 * B * (N + S) + 4 * B * S * sum(Ks), 8 * B * S * N
+    if name == "fps_ball_query":
+        N, S = int(kv["N"]), int(kv["M"])
+        Ks = [int(k) for k in kv["K"].split("/")]
+        return 12 * B * N + 16 * B * S + 12 * B * (N + S) + 4 * B * S * sum(Ks), 8 * B * N * (S - 1) + 8 * B * S * N
     if name == "fps_gather":
         N, M = int(kv["N"]), int(kv["M"])
         return 12 * B * N + 4 * B * M + 12 * B * M, 8 * B * N * (M - 1)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "three_interpolate_grad_kernel_launcher_fast": [c_int] * 4 + [_P, _P, _P, _P, _P],
     "captra_ball_query_multi": [c_int] * 4 + [_P, _P, _P, _P, _P, _P],
     "captra_ball_query_group": [c_int] * 4 + [c_float, c_int] + [_P] * 6,
+    "captra_fps_ball_query": [c_int] * 3 + [_P, _P, _P, c_int, _P, _P, _P, _P, _P],
     "captra_fps_gather": [c_int] * 3 + [_P, _P, _P, _P, _P],
     "captra_three_nn_interpolate": [c_int] * 4 + [_P] * 7 + [c_int, c_i64, c_int, _P],
     "captra_mlp_pack": [_P, c_int, _P, _P],

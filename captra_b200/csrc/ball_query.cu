@@ -29,14 +29,20 @@ struct BQParams {
     int *idx[CAPTRA_MAX_RADII];
 };
 
-template <int NR, int CPW>
+// PIPED: the centroids are being produced by a furthest-point-sampling kernel that is still running
+// (captra_fps_ball_query): the grid is laid out (cloud, centroid block) so that blocks become resident in the order
+// FPS finishes them, a CTA stages its cloud tile first and only then waits until `progress[b]` covers its centroids,
+// and the centroids are read past the (non-coherent) L1.
+template <int NR, int CPW, bool PIPED>
 __global__ void __launch_bounds__(BQ_THREADS)
-ball_query_kernel(int n, int m, BQParams prm, const float *__restrict__ new_xyz,
-                  const float *__restrict__ xyz) {
+ball_query_kernel(int n, int m, BQParams prm, const float *__restrict__ new_xyz_,
+                  const float *__restrict__ xyz, const int *progress) {
     extern __shared__ float smem[];
     float *sx = smem, *sy = smem + BQ_PLANE, *sz = smem + 2 * BQ_PLANE;
+    const float *new_xyz = new_xyz_;
 
-    const int b = blockIdx.y;
+    const int b = PIPED ? blockIdx.x : blockIdx.y;
+    const int cblock = PIPED ? blockIdx.y : blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const float *cloud = xyz + (size_t)b * n * 3;
@@ -45,13 +51,31 @@ ball_query_kernel(int n, int m, BQParams prm, const float *__restrict__ new_xyz,
     float cx[CPW], cy[CPW], cz[CPW];
     int cnt[CPW][NR], first[CPW][NR];
     int *row[CPW][NR];
-    const int c0 = (blockIdx.x * BQ_WARPS + warp) * CPW;
+    const int c0 = (cblock * BQ_WARPS + warp) * CPW;
+    if (PIPED) {
+        // stage the first cloud tile while FPS is still picking this block's centroids
+        const int tn0 = min(BQ_TILE, n);
+        for (int e = threadIdx.x; e < tn0 * 3; e += BQ_THREADS) {
+            const int pt = e / 3, comp = e - pt * 3;
+            smem[comp * BQ_PLANE + pt] = __ldg(cloud + e);
+        }
+        if (threadIdx.x == 0) {
+            const int need = min(m, (cblock + 1) * BQ_WARPS * CPW);
+            int have;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(have) : "l"(progress + b) : "memory");
+                if (have < need) __nanosleep(500);
+            } while (have < need);
+        }
+        __syncthreads();
+    }
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
         const int ci = c0 + c;
         const bool ok = ci < m;
         const float *p = new_xyz + ((size_t)b * m + (ok ? ci : 0)) * 3;
-        cx[c] = p[0]; cy[c] = p[1]; cz[c] = p[2];
+        if (PIPED) { cx[c] = __ldcg(p); cy[c] = __ldcg(p + 1); cz[c] = __ldcg(p + 2); }
+        else { cx[c] = p[0]; cy[c] = p[1]; cz[c] = p[2]; }
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             cnt[c][r] = ok ? 0 : prm.nsample[r];  // out-of-range centroids start "full"
@@ -63,13 +87,15 @@ ball_query_kernel(int n, int m, BQParams prm, const float *__restrict__ new_xyz,
     for (int tile0 = 0; tile0 < n; tile0 += BQ_TILE) {
         const int tn = min(BQ_TILE, n - tile0);
         if (tile0 > 0) __syncthreads();
-        // coalesced AoS read, SoA store
-        const float *src = cloud + (size_t)tile0 * 3;
-        for (int e = threadIdx.x; e < tn * 3; e += BQ_THREADS) {
-            const int pt = e / 3, comp = e - pt * 3;
-            smem[comp * BQ_PLANE + pt] = __ldg(src + e);
+        if (!PIPED || tile0 > 0) {      // (PIPED: the first tile was staged before the wait)
+            // coalesced AoS read, SoA store
+            const float *src = cloud + (size_t)tile0 * 3;
+            for (int e = threadIdx.x; e < tn * 3; e += BQ_THREADS) {
+                const int pt = e / 3, comp = e - pt * 3;
+                smem[comp * BQ_PLANE + pt] = __ldg(src + e);
+            }
+            __syncthreads();
         }
-        __syncthreads();
 
         bool warp_active = false;
 #pragma unroll
@@ -123,14 +149,33 @@ ball_query_kernel(int n, int m, BQParams prm, const float *__restrict__ new_xyz,
 
 template <int NR>
 static int launch_bq(int b, int n, int m, const BQParams &prm, const float *new_xyz,
-                     const float *xyz, cudaStream_t stream) {
+                     const float *xyz, cudaStream_t stream, const int *progress = nullptr) {
     constexpr int CPW = 4;
-    auto kern = ball_query_kernel<NR, CPW>;
     const size_t smem = sizeof(float) * 3 * BQ_PLANE;
+    if (progress) {
+        // programmatic dependent launch: this grid may start while the preceding kernel of the stream (FPS, which
+        // has signalled griddepcontrol.launch_dependents) is still running; the data dependency is the progress counter
+        auto kern = ball_query_kernel<NR, CPW, true>;
+        CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(b, ceil_div(m, BQ_WARPS * CPW));
+        cfg.blockDim = dim3(BQ_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CAPTRA_CUDA(cudaLaunchKernelEx(&cfg, kern, n, m, prm, new_xyz, xyz, progress));
+        CAPTRA_CHECK_LAUNCH("ball_query(piped)");
+        return CAPTRA_OK;
+    }
+    auto kern = ball_query_kernel<NR, CPW, false>;
     // per-device attribute, cheap host-side call: set it on every launch (no process-wide flag)
     CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(m, BQ_WARPS * CPW), b);
-    kern<<<grid, BQ_THREADS, smem, stream>>>(n, m, prm, new_xyz, xyz);
+    kern<<<grid, BQ_THREADS, smem, stream>>>(n, m, prm, new_xyz, xyz, nullptr);
     CAPTRA_CHECK_LAUNCH("ball_query");
     return CAPTRA_OK;
 }
@@ -502,6 +547,39 @@ extern "C" int captra_ball_query_multi(int b, int n, int m, int nradii, const fl
         case 2: return launch_bq<2>(b, n, m, prm, new_xyz, xyz, s);
         case 3: return launch_bq<3>(b, n, m, prm, new_xyz, xyz, s);
         default: return launch_bq<4>(b, n, m, prm, new_xyz, xyz, s);
+    }
+}
+
+// in fps.cu: FPS that publishes its progress (see captra_fps_ball_query)
+namespace captra {
+int fps_gather_progress(int b, int n, int m, const float *dataset, int *idxs, float *new_xyz, int *progress, cudaStream_t stream);
+}
+
+extern "C" int captra_fps_ball_query(int b, int n, int m, const float *xyz, int *fps_idx, float *new_xyz, int nradii,
+                                     const float *radii_host, const int *nsamples_host, int *const *idx_host_ptrs,
+                                     int *progress, captra_stream_t stream) {
+    CAPTRA_REQUIRE(b >= 0 && n >= 1 && m >= 1, "fps_ball_query: bad sizes");
+    CAPTRA_REQUIRE(nradii >= 1 && nradii <= CAPTRA_MAX_RADII, "fps_ball_query: nradii must be 1..%d", CAPTRA_MAX_RADII);
+    CAPTRA_REQUIRE(b <= 65535 && n <= 8192, "fps_ball_query: at most 65535 clouds of at most 8192 points (use the two separate calls beyond)");
+    if (b == 0) return CAPTRA_OK;
+    CAPTRA_REQUIRE(xyz && fps_idx && new_xyz && progress, "fps_ball_query: null pointer");
+    BQParams prm;
+    for (int r = 0; r < CAPTRA_MAX_RADII; ++r) {
+        const int rr = r < nradii ? r : 0;
+        const float rad = radii_host[rr];
+        prm.radius2[r] = rad * rad;
+        prm.nsample[r] = nsamples_host[rr];
+        prm.idx[r] = idx_host_ptrs[rr];
+        CAPTRA_REQUIRE(prm.nsample[r] >= 0 && (prm.nsample[r] == 0 || prm.idx[r]), "fps_ball_query: bad nsample/idx for radius %d", rr);
+    }
+    cudaStream_t s = as_stream(stream);
+    int rc = fps_gather_progress(b, n, m, xyz, fps_idx, new_xyz, progress, s);
+    if (rc) return rc;
+    switch (nradii) {
+        case 1: return launch_bq<1>(b, n, m, prm, new_xyz, xyz, s, progress);
+        case 2: return launch_bq<2>(b, n, m, prm, new_xyz, xyz, s, progress);
+        case 3: return launch_bq<3>(b, n, m, prm, new_xyz, xyz, s, progress);
+        default: return launch_bq<4>(b, n, m, prm, new_xyz, xyz, s, progress);
     }
 }
 

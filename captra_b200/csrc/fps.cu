@@ -32,11 +32,16 @@ __device__ __forceinline__ unsigned tie_key(int k, int ref_mask, int ref_shift) 
     return ~((rev << 22) | (unsigned)k);
 }
 
+// progress != null (captra_fps_ball_query): the kernel lets its stream successor start early (programmatic dependent
+// launch) and publishes, every FPS_PUBLISH rounds, how many centroids of the cloud are final (release store after the
+// writer's own new_xyz stores), so that a ball query can consume them while the sampling goes on.
+constexpr int FPS_PUBLISH = 32;
 template <int NT, int PPT>
 __global__ void __launch_bounds__(NT)
 fps_reg_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
-               float *__restrict__ temp, int *__restrict__ idxs, float *__restrict__ new_xyz) {
+               float *__restrict__ temp, int *__restrict__ idxs, float *__restrict__ new_xyz, int *progress) {
     extern __shared__ float smem[];  // sx[n] sy[n] sz[n]
+    if (progress) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ uint2 rec[2][32];
     constexpr int NW = NT / 32;
 
@@ -103,8 +108,11 @@ fps_reg_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,
         if (tid == 0) {
             out[r] = old;
             if (oxyz) { oxyz[r * 3 + 0] = ox; oxyz[r * 3 + 1] = oy; oxyz[r * 3 + 2] = oz; }
+            if (progress && ((r + 1) % FPS_PUBLISH == 0 || r == m - 1))
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + b), "r"(r + 1) : "memory");
         }
     }
+    if (progress && m == 1 && tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + b), "r"(1) : "memory");
 
     // the reference leaves its running min-distances in the caller's scratch
     if (tmp) {
@@ -355,15 +363,32 @@ static int launch_fps_cluster(int b, int n, int m, int ref_bits, const float *da
 
 template <int NT, int PPT>
 static int launch_fps_reg(int b, int n, int m, int ref_bits, const float *dataset, float *temp,
-                          int *idxs, float *new_xyz, cudaStream_t stream) {
+                          int *idxs, float *new_xyz, cudaStream_t stream, int *progress = nullptr) {
     auto kern = fps_reg_kernel<NT, PPT>;
     const size_t smem = sizeof(float) * 3 * (size_t)n;
     // static smem (the records) counts against the 48 KB default; opting in needs a value > 48 KB
     if (smem + 1024 > 48 * 1024)
         CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
-    kern<<<b, NT, smem, stream>>>(n, m, ref_bits, dataset, temp, idxs, new_xyz);
+    kern<<<b, NT, smem, stream>>>(n, m, ref_bits, dataset, temp, idxs, new_xyz, progress);
     CAPTRA_CHECK_LAUNCH("furthest_point_sampling");
     return CAPTRA_OK;
+}
+
+static int fps_ref_bits(int n) {
+    int ref_bits = 0;
+    while ((2 << ref_bits) <= n && ref_bits < 10) ++ref_bits;
+    return ref_bits;
+}
+
+// FPS + gather with progress publication (register-resident shapes only: n <= 8192); progress [b] must be zero
+int fps_gather_progress(int b, int n, int m, const float *dataset, int *idxs, float *new_xyz, int *progress, cudaStream_t s) {
+    const int ref_bits = fps_ref_bits(n);
+    if (n <= 128) return launch_fps_reg<32, 4>(b, n, m, ref_bits, dataset, nullptr, idxs, new_xyz, s, progress);
+    if (n <= 512) return launch_fps_reg<128, 4>(b, n, m, ref_bits, dataset, nullptr, idxs, new_xyz, s, progress);
+    if (n <= 1024) return launch_fps_reg<256, 4>(b, n, m, ref_bits, dataset, nullptr, idxs, new_xyz, s, progress);
+    if (n <= 2048) return launch_fps_reg<256, 8>(b, n, m, ref_bits, dataset, nullptr, idxs, new_xyz, s, progress);
+    if (n <= 4096) return launch_fps_reg<512, 8>(b, n, m, ref_bits, dataset, nullptr, idxs, new_xyz, s, progress);
+    return launch_fps_reg<1024, 8>(b, n, m, ref_bits, dataset, nullptr, idxs, new_xyz, s, progress);
 }
 
 }  // namespace captra

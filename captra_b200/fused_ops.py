@@ -45,6 +45,29 @@ def ball_query_multi(radii, nsamples, xyz, new_xyz):
     return outs
 
 
+def fps_ball_query(xyz, npoint, radii, nsamples):
+    """FPS and the multi-radius ball query around its picks as one pipelined call (captra_fps_ball_query):
+    xyz [B,N,3] -> (new_xyz [B,npoint,3], [idx [B,npoint,K_r] int32 per radius]); N <= 8192."""
+    B, N, _ = xyz.shape
+    nr = len(radii)
+    tot = B * npoint * sum(int(k) for k in nsamples)
+    flat = torch.zeros(tot + B, dtype=_i32, device=xyz.device)      # one fill: the index lists (empty balls keep zeros) + the progress counters
+    outs, off = [], 0
+    for k in nsamples:
+        outs.append(flat[off:off + B * npoint * int(k)].view(B, npoint, int(k)))
+        off += B * npoint * int(k)
+    progress = flat[tot:]
+    fps_idx = torch.empty(B, npoint, dtype=_i32, device=xyz.device)
+    new_xyz = torch.empty(B, npoint, 3, dtype=_f32, device=xyz.device)
+    ra = (ctypes.c_float * nr)(*[float(r) for r in radii])
+    ka = (ctypes.c_int * nr)(*[int(k) for k in nsamples])
+    pa = (ctypes.c_void_p * nr)(*[o.data_ptr() for o in outs])
+    _lib.call("fps_ball_query[B=%d,N=%d,M=%d,K=%s]" % (B, N, npoint, "/".join(map(str, nsamples))), _lib.load().captra_fps_ball_query,
+              B, N, npoint, _lib.ptr(xyz, _f32, "xyz"), fps_idx.data_ptr(), new_xyz.data_ptr(), nr, ra, ka, pa, progress.data_ptr(),
+              _lib.stream_ptr(xyz.device), device=xyz.device)
+    return new_xyz, outs
+
+
 def ball_query_group(radius, nsample, xyz, new_xyz, features):
     """QueryAndGroup without the concat (pointnet2_utils.py:290-296): xyz [B,N,3], new_xyz [B,M,3], features [B,C,N]
     -> (idx [B,M,K] int32, grouped [B,C,M,K]); one C-ABI call (captra_ball_query_group)."""

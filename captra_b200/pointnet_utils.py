@@ -237,8 +237,12 @@ class PointNetSetAbstractionMsg(nn.Module):
         if geom is not None and "new_xyz" in geom:
             new_xyz, idxs = geom["new_xyz"], geom["idxs"]
         else:
-            _, new_xyz = fused_ops.fps_gather(xyz_pm, self.npoint)
-            idxs = fused_ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_pm, new_xyz)
+            if xyz_pm.shape[1] <= 8192 and os.environ.get("CAPTRA_FPS_BQ_PIPE", "1") != "0":   # knob: A/B timing
+                # sampling and grouping indices as a pipeline: the ball query consumes centroids while FPS still picks
+                new_xyz, idxs = fused_ops.fps_ball_query(xyz_pm, self.npoint, self.radius_list, self.nsample_list)
+            else:
+                _, new_xyz = fused_ops.fps_gather(xyz_pm, self.npoint)
+                idxs = fused_ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_pm, new_xyz)
             if geom is not None:
                 geom["new_xyz"], geom["idxs"] = new_xyz, idxs
         out = torch.empty(xyz_pm.shape[0], self.npoint, self.out_channel, dtype=torch.float32, device=xyz_pm.device)

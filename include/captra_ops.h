@@ -117,6 +117,16 @@ int captra_ball_query_group(int b, int n, int m, int c, float radius, int nsampl
 int captra_fps_gather(int b, int n, int m, const float *dataset, float *temp, int *idxs,
                       float *new_xyz, captra_stream_t stream);
 
+/* The sampling + grouping-index step of an MSG set-abstraction layer (pointnet_utils.py:225-233) as a PIPELINE: FPS
+ * (-> fps_idx [B,M], new_xyz [B,M,3]) and the multi-radius ball query around the sampled centroids run CONCURRENTLY.
+ * FPS is a latency chain that keeps one SM per cloud busy; it publishes every 32 rounds how many centroids are
+ * final (progress [B] ints, zeroed by the caller) and lets its stream successor start early (programmatic dependent
+ * launch); the ball query's blocks, laid out in the order FPS completes them, wait on that counter.  Results are
+ * identical to captra_fps_gather followed by captra_ball_query_multi.  n <= 8192; idx buffers zeroed by the caller. */
+int captra_fps_ball_query(int b, int n, int m, const float *xyz, int *fps_idx, float *new_xyz, int nradii,
+                          const float *radii_host, const int *nsamples_host, int *const *idx_host_ptrs,
+                          int *progress, captra_stream_t stream);
+
 /* three_nn + inverse-distance weights (pointnet_utils.py:284-287) + three_interpolate:
  * out[., i] = sum_j w_j * points[., idx_j].  idx and weight [B,n,3] are required scratch /
  * outputs; dist (the sqrt'ed distance ThreeNN returns, pointnet2_utils.py:134) may be NULL.

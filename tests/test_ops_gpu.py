@@ -324,3 +324,42 @@ def test_backward_ops_are_deterministic_and_correctly_rounded(cuda):
     P.gather_points_grad_wrapper(B, C, N, M, g2, sidx, a)
     P.gather_points_grad_wrapper(B, C, N, M, g2, sidx, b)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,N,M,radii,ks,kind", [(32, 4096, 512, [0.05, 0.1, 0.2], [32, 64, 128], "surface"), (5, 512, 128, [0.2, 0.4], [64, 128], "surface"),
+                                                   (3, 1000, 77, [0.15], [16], "uniform"), (2, 4096, 2000, [0.05, 0.3], [8, 32], "tiled"),
+                                                   (70, 300, 33, [0.1, 0.2, 0.3, 0.4], [4, 8, 16, 32], "uniform")])
+def test_fps_ball_query_pipeline(B, N, M, radii, ks, kind, oracle, cuda):
+    """captra_fps_ball_query: FPS and the multi-radius ball query overlapped through a progress counter and a
+    programmatic dependent launch -- bit-identical to the two separate ops (and the oracle), also when replayed
+    from a CUDA graph and with more ball-query blocks than fit the GPU at once (B = 70)."""
+    from captra_b200 import fused_ops
+    if kind == "surface":
+        pts = synthetic.batch_surface_box(B, N, seed=B + N)[0]
+    elif kind == "tiled":
+        pts = synthetic.batch_tiled(B, N, 1500, seed=N)
+    else:
+        pts = synthetic.batch_uniform(B, N, seed=N)
+    x = dev(pts, cuda)
+    new_xyz, idxs = fused_ops.fps_ball_query(x, M, radii, ks)
+    _, want_xyz = fused_ops.fps_gather(x, M)
+    want_idx = fused_ops.ball_query_multi(radii, ks, x, want_xyz)
+    assert torch.equal(new_xyz, want_xyz)
+    for got, want, r, k in zip(idxs, want_idx, radii, ks):
+        assert torch.equal(got, want)
+        if B <= 5:
+            assert np.array_equal(got.cpu().numpy(), oracle.ball_query(r, k, pts, want_xyz.cpu().numpy()))
+    # replayed from a graph
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fused_ops.fps_ball_query(x, M, radii, ks)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        gx, gi = fused_ops.fps_ball_query(x, M, radii, ks)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(gx, want_xyz) and all(torch.equal(a, b) for a, b in zip(gi, want_idx))
