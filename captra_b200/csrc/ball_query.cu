@@ -153,6 +153,9 @@ static int launch_bq(int b, int n, int m, const BQParams &prm, const float *new_
     constexpr int CPW = 4;
     const size_t smem = sizeof(float) * 3 * BQ_PLANE;
     if (progress) {
+        // two centroids per warp here (16 per CTA): the blocks that become ready last -- when FPS has already finished --
+        // are the tail of the pipeline, and a block's latency is proportional to the centroids a warp walks serially
+        constexpr int CPW = 2;
         // programmatic dependent launch: this grid may start while the preceding kernel of the stream (FPS, which
         // has signalled griddepcontrol.launch_dependents) is still running; the data dependency is the progress counter
         auto kern = ball_query_kernel<NR, CPW, true>;

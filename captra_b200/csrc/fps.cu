@@ -33,9 +33,9 @@ __device__ __forceinline__ unsigned tie_key(int k, int ref_mask, int ref_shift) 
 }
 
 // progress != null (captra_fps_ball_query): the kernel lets its stream successor start early (programmatic dependent
-// launch) and publishes, every FPS_PUBLISH rounds, how many centroids of the cloud are final (release store after the
+// launch) and publishes, every FPS_PUBLISH rounds (one block of the piped ball query), how many centroids of the cloud are final (release store after the
 // writer's own new_xyz stores), so that a ball query can consume them while the sampling goes on.
-constexpr int FPS_PUBLISH = 32;
+constexpr int FPS_PUBLISH = 16;
 template <int NT, int PPT>
 __global__ void __launch_bounds__(NT)
 fps_reg_kernel(int n, int m, int ref_bits, const float *__restrict__ dataset,

@@ -119,7 +119,7 @@ int captra_fps_gather(int b, int n, int m, const float *dataset, float *temp, in
 
 /* The sampling + grouping-index step of an MSG set-abstraction layer (pointnet_utils.py:225-233) as a PIPELINE: FPS
  * (-> fps_idx [B,M], new_xyz [B,M,3]) and the multi-radius ball query around the sampled centroids run CONCURRENTLY.
- * FPS is a latency chain that keeps one SM per cloud busy; it publishes every 32 rounds how many centroids are
+ * FPS is a latency chain that keeps one SM per cloud busy; it publishes every 16 rounds how many centroids are
  * final (progress [B] ints, zeroed by the caller) and lets its stream successor start early (programmatic dependent
  * launch); the ball query's blocks, laid out in the order FPS completes them, wait on that counter.  Results are
  * identical to captra_fps_gather followed by captra_ball_query_multi.  n <= 8192; idx buffers zeroed by the caller. */
