@@ -49,7 +49,7 @@ if _REFERENCE_ARM:
 _nd = os.environ.get("NCCL_DEBUG", "").upper()
 if _nd in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
-elif "NCCL_DEBUG_FILE" not in os.environ:
+if "NCCL_DEBUG_FILE" not in os.environ:      # (WARN still prints the version banner)
     os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
 sys.path.insert(0, ROOT)
 

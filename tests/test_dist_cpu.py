@@ -24,6 +24,32 @@ def test_shard_range_covers_everything():
     assert [shard.category_of(i) for i in range(8)] == [0, 1, 2, 3, 4, 5, 0, 1]
 
 
+def test_cfg4_sharding_and_category_grouping():
+    """BASELINE cfg4 host logic: 256 trajectories, category = global index mod 6, contiguous shards, grouped by category
+    inside a rank.  Whatever the number of ranks, every trajectory is tracked exactly once with its own category."""
+    from captra_b200 import track
+    total = 256
+    want = {}
+    for i in range(total):
+        want[track.NOCS_CATEGORIES[shard.category_of(i)]] = want.get(track.NOCS_CATEGORIES[shard.category_of(i)], 0) + 1
+    for world in (1, 2, 4, 8, 3):
+        seen, got = [], {}
+        for rank in range(world):
+            a, b = shard.shard_range(total, world, rank)
+            ids = [shard.category_of(i) for i in range(a, b)]
+            order, names = track.group_by_category(ids)
+            assert sorted(order) == list(range(b - a))
+            assert [track.NOCS_CATEGORIES[ids[i]] for i in order] == names           # the permutation groups, it does not relabel
+            assert names == sorted(names, key=track.NOCS_CATEGORIES.index)           # contiguous spans, one per category
+            seen += [a + i for i in order]
+            for n in names:
+                got[n] = got.get(n, 0) + 1
+        assert sorted(seen) == list(range(total)) and got == want
+    assert set(want) == set(track.NOCS_CATEGORIES) and all(track.CATEGORIES[c]["num_parts"] == 1 for c in want)
+    # obj_info_nocs.yml: bottle, bowl, can are symmetric; camera, laptop, mug are not
+    assert [track.CATEGORIES[c]["sym"] for c in track.NOCS_CATEGORIES] == [True, True, False, True, False, False]
+
+
 def _poses(n, seed):
     g = torch.Generator().manual_seed(seed)
     mk = lambda: {"rotation": torch.randn(n, 2, 3, 3, generator=g), "translation": torch.randn(n, 2, 3, 1, generator=g),

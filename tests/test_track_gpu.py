@@ -197,3 +197,30 @@ def test_graphed_step_equals_eager_and_no_overflow(category, cuda):
     for k in want2:
         assert torch.equal(got2[k], want2[k]), k
     assert not mlp.f16_overflowed()
+
+
+def test_mixed_tracker_equals_per_category_runs(cuda):
+    """BASELINE cfg4: a batch of several NOCS categories (grouped by category inside the rank) through MixedTracker is
+    bit-identical to running every category's Tracker alone on its slice -- eagerly and from one CUDA graph."""
+    from captra_b200 import shard, track
+    ids = [shard.category_of(i) for i in range(40, 53)]                 # a rank's contiguous shard: category = global index mod 6
+    order, names = track.group_by_category(ids)
+    assert sorted(order) == list(range(len(ids))) and names == sorted(names, key=track.NOCS_CATEGORIES.index)
+    mt = track.MixedTracker(names, device=cuda, seed=0).to(cuda).eval()
+    parts = []
+    for j, (c, a, b) in enumerate(mt.spans):
+        parts.append(track.synthetic_track_batch(b - a, c, n=4096, seed=50 + j))
+    cat = lambda f: torch.from_numpy(np.concatenate([f(p) for p in parts], 0)).to(cuda)
+    pts, mean = cat(lambda p: p["points"]), cat(lambda p: p["points_mean"])
+    pose = {k: cat(lambda p: p["pose"][k]) for k in parts[0]["pose"]}
+    got = {k: v.clone() for k, v in mt.step(pts, mean, pose).items()}
+    for c, a, b in mt.spans:
+        alone = track.Tracker(track.make_cfg(c, device=str(cuda)), seed=10 * (list(track.CATEGORIES).index(c) + 1)).to(cuda).eval()
+        want = alone.step(pts[a:b], mean[a:b], {k: v[a:b] for k, v in pose.items()})
+        for k in want:
+            assert torch.equal(got[k][a:b], want[k]), (c, k)
+    gs = track.GraphedStep(mt, pts, mean, pose)
+    out = gs(pts, mean, pose)
+    for k in got:
+        assert torch.equal(out[k], got[k]), k
+    assert len({c for c, _, _ in mt.spans}) == 6 and set(got) == {"rotation", "scale", "translation"}
