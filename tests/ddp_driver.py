@@ -36,7 +36,7 @@ for step in range(2):
            "init_part": {k: torch.from_numpy(v).to(dev) for k, v in b["pose"].items()}}
     inp["canon_pose"] = {k: inp["init_part"][k][:, 0] for k in ("rotation", "translation", "scale")}
     pred = ddp(inp)
-    loss = (pred["nocs"] ** 2).mean() + pred["part"]["scale"].sum() + pred["part"]["translation"].abs().sum()
+    loss = (pred["nocs"] ** 2).mean() + pred["seg"][:, 0].mean() + pred["part"]["scale"].sum() + pred["part"]["translation"].abs().sum()
     opt.zero_grad()
     loss.backward()
     opt.step()
