@@ -18,7 +18,7 @@
  * Parity pin: the reference ships no golden vectors.  This oracle is
  * pinned against the reference's own kernels compiled from /root/reference into
  * oracle/_ref/libpointnet2_ref.so (see oracle/Makefile) and run on the GPU box
- * (tests/test_ops_gpu.py::test_oracle_matches_reference_kernels), and against fixtures
+ * (the `refcu` comparisons of tests/test_ops_gpu.py: test_fps_bit_exact, test_ball_query_bit_exact, test_group_gather_bit_exact, test_three_nn_interpolate_bit_exact, test_knn_bit_exact, test_backward_ops), and against fixtures
  * generated here by importing the Python reference (tests/golden/).
  */
 #include <math.h>

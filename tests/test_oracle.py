@@ -1,7 +1,7 @@
 """CPU tests: pin oracle/cpu_ref against (i) fixtures produced by the reference's own Python code
 (tests/golden/make_golden.py), (ii) independent numpy statements of each op's rule.  The pin
 against the reference's CUDA kernels themselves (oracle/_ref) runs on the GPU box
-(tests/test_ops_gpu.py::test_oracle_matches_reference_kernels)."""
+(the `refcu` comparisons of tests/test_ops_gpu.py: test_fps_bit_exact, test_ball_query_bit_exact, test_group_gather_bit_exact, test_three_nn_interpolate_bit_exact, test_knn_bit_exact, test_backward_ops)."""
 import os
 
 import numpy as np
