@@ -283,7 +283,8 @@ class GraphedStep:
         flag is always checked once here, after the warm-up frames."""
         from . import _lib, mlp
         self.check_every, self._replays = int(check_every), 0
-        mlp.f16_overflowed(reset=True) if mlp.DEFAULT_IMPL == 2 else None
+        if mlp.DEFAULT_IMPL == 2:
+            mlp.f16_overflowed(reset=True)
         self.inp = {"points": points.clone(), "points_mean": points_mean.clone(),
                     "pose": {k: v.clone() for k, v in pose.items()}}
         self.gt = {k: v.clone().float() for k, v in gt.items()} if gt is not None else None
