@@ -5,6 +5,8 @@ Eval-mode forward = 13 kernel launches on point-major tensors: 2x (FPS+gather, m
 query), 5 fused SA scales, group-all SA, fp3, 2x (3-NN+interpolate, FP MLP) with conv1/bn1 folded
 into the fp1 chain as a third layer.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -64,6 +66,17 @@ class PointNet2Msg(nn.Module):
         g = (lambda k: geom.setdefault(k, {})) if geom is not None else (lambda k: None)
         l0_xyz = xyz_pm if xyz_pm is not None else input.transpose(1, 2).contiguous()   # [B,N,3]
         l0_feats = l0_xyz if self.use_xyz_feat else None                   # backbones.py:57-60
+        aux = getattr(geom, "aux", None)
+        if aux is not None and os.environ.get("CAPTRA_GEOM_AUX", "1") != "0":
+            # The second level's sampling + grouping indices depend on the first level's CENTROIDS only, not on its
+            # features: run them on a helper stream, beside the first level's MLPs (FPS keeps one small CTA per cloud
+            # busy for 128 dependent rounds).  SharedGeom's events order producer and consumers across the streams.
+            g1, g2 = g("sa1"), g("sa2")
+            if "new_xyz" not in g1:
+                g1["new_xyz"], g1["idxs"] = self.sa1.geometry(l0_xyz)
+            if "new_xyz" not in g2:
+                with torch.cuda.stream(aux):
+                    g2["new_xyz"], g2["idxs"] = self.sa2.geometry(g1["new_xyz"])
         l1_xyz, l1_feats = self.sa1.forward_pm(l0_xyz, l0_feats, geom=g("sa1"))
         l2_xyz, l2_feats = self.sa2.forward_pm(l1_xyz, l1_feats, geom=g("sa2"))
         l3_feats = self.sa3.forward_pm(l2_xyz, l2_feats)                   # [B,1024]

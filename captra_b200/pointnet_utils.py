@@ -118,9 +118,10 @@ class SharedGeom(dict):
     from another stream makes that stream wait for the event.  The producer's launches must be enqueued (host side)
     before the consumer asks; on the device the two chains then overlap wherever the data dependencies allow."""
 
-    def __init__(self):
+    def __init__(self, aux=None):
         super().__init__()
         self._ev = {}
+        self.aux = aux          # optional helper stream: the second SA level's sampling / grouping runs there, beside the first level's MLPs
 
     def __setitem__(self, key, value):
         super().__setitem__(key, value)
@@ -140,7 +141,7 @@ class SharedGeom(dict):
 
     def setdefault(self, key, default=None):
         if key not in self:
-            super().__setitem__(key, SharedGeom() if isinstance(default, dict) and not default else default)
+            super().__setitem__(key, SharedGeom(self.aux) if isinstance(default, dict) and not default else default)
         return super().__getitem__(key)
 
 
@@ -226,6 +227,14 @@ class PointNetSetAbstractionMsg(nn.Module):
             return proj, scales
         return self._cache_pre.get(self, build)
 
+    def geometry(self, xyz_pm):
+        """The coordinate-only part of the layer (pointnet_utils.py:225-233): xyz [B,N,3] -> (new_xyz [B,S,3], [idx [B,S,K_r]])."""
+        if xyz_pm.shape[1] <= 8192 and os.environ.get("CAPTRA_FPS_BQ_PIPE", "1") != "0":   # knob: A/B timing
+            # sampling and grouping indices as a pipeline: the ball query consumes centroids while FPS still picks
+            return fused_ops.fps_ball_query(xyz_pm, self.npoint, self.radius_list, self.nsample_list)
+        _, new_xyz = fused_ops.fps_gather(xyz_pm, self.npoint)
+        return new_xyz, fused_ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_pm, new_xyz)
+
     def forward_pm(self, xyz_pm, feats_pm, geom=None):
         """Fused inference path on point-major tensors: xyz [B,N,3], feats [B,N,D] or None ->
         (new_xyz [B,S,3], new_feats [B,S,sum(cout)]).  `geom` (a dict) carries the sampling and
@@ -237,12 +246,7 @@ class PointNetSetAbstractionMsg(nn.Module):
         if geom is not None and "new_xyz" in geom:
             new_xyz, idxs = geom["new_xyz"], geom["idxs"]
         else:
-            if xyz_pm.shape[1] <= 8192 and os.environ.get("CAPTRA_FPS_BQ_PIPE", "1") != "0":   # knob: A/B timing
-                # sampling and grouping indices as a pipeline: the ball query consumes centroids while FPS still picks
-                new_xyz, idxs = fused_ops.fps_ball_query(xyz_pm, self.npoint, self.radius_list, self.nsample_list)
-            else:
-                _, new_xyz = fused_ops.fps_gather(xyz_pm, self.npoint)
-                idxs = fused_ops.ball_query_multi(self.radius_list, self.nsample_list, xyz_pm, new_xyz)
+            new_xyz, idxs = self.geometry(xyz_pm)
             if geom is not None:
                 geom["new_xyz"], geom["idxs"] = new_xyz, idxs
         out = torch.empty(xyz_pm.shape[0], self.npoint, self.out_channel, dtype=torch.float32, device=xyz_pm.device)

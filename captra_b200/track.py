@@ -160,10 +160,11 @@ class Tracker(torch.nn.Module):
     # fp3 layers: 32 tiles for 148 SMs).  CAPTRA_TWO_STREAM=0 runs the two networks back to back (A/B knob).
     TWO_STREAM = os.environ.get("CAPTRA_TWO_STREAM", "1") != "0"
 
-    def _side_stream(self, device):
-        if device not in self._side:
-            self._side[device] = torch.cuda.Stream(device)
-        return self._side[device]
+    def _side_stream(self, key):
+        """key: a device, or (device, name) for the helper streams."""
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(key[0] if isinstance(key, tuple) else key)
+        return self._side[key]
 
     def _step_two_stream(self, points, points_mean, last_pose, canon):
         from . import frame_ops
@@ -171,8 +172,11 @@ class Tracker(torch.nn.Module):
         P, B = self.num_parts, points.shape[0]
         main = torch.cuda.current_stream(points.device)
         side = self._side_stream(points.device)
-        geom = SharedGeom() if P == 1 else None
-        side.wait_stream(main)                      # the frame's inputs
+        aux_a, aux_b = self._side_stream((points.device, "aux_a")), self._side_stream((points.device, "aux_b"))
+        geom = SharedGeom(aux_a)                    # the CoordNet's geometry (shared with the RotationNet for a rigid object)
+        geom_b = geom if P == 1 else SharedGeom(aux_b)
+        for st in (side, aux_a, aux_b):
+            st.wait_stream(main)                    # the frame's inputs
         # CoordNet on the current stream; every coordinate-only result it produces carries an event
         pred = self.npcs_net({"points": points, "points_mean": points_mean, "canon_pose": canon, "geom": geom})
         with torch.cuda.stream(side):
@@ -181,8 +185,9 @@ class Tracker(torch.nn.Module):
             else:
                 flat = {k: last_pose[k].reshape((-1,) + last_pose[k].shape[2:]) for k in ("rotation", "translation", "scale")}
                 xyz_pm = frame_ops.canonicalize(points, points_mean, flat["rotation"], flat["translation"], flat["scale"], parts=P)[0]
-            raws = self.net.regress_net.forward_heads(xyz_pm, B, geom=geom)
-        main.wait_stream(side)
+            raws = self.net.regress_net.forward_heads(xyz_pm, B, geom=geom_b)
+        for st in (side, aux_a, aux_b):
+            main.wait_stream(st)
         return pred, raws
 
     @torch.no_grad()
