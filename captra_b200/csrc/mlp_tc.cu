@@ -758,7 +758,8 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                 // <= 8 input channels: one slab, the row comes assembled from the metadata ring (straight-line code:
                 // no prefetch buffers, no loops -- these launches are instruction-issue bound)
                 const int kstore = (a.kreal[0] + KMMA - 1) / KMMA * KMMA;
-                acquire(it);
+                // no acquire: the previous tile's last epilogue waited for d_ready, i.e. for EVERY MMA issued so far, so
+                // all stages are free at a tile boundary (the same holds for the first NST slabs of any layer, below)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int c0 = 8 * unit_idx(u);
@@ -788,7 +789,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                     for (int u = 0; u < 2; ++u) load_unit(RS == 2 ? u : 0, s * KC + 8 * unit_idx(u), buf[u]);
                 };
                 auto step = [&](int s, float (&buf)[2][8]) {   // buf holds slab s and is refilled with slab s + PF
-                    acquire(it);
+                    if (s >= (int)NST) acquire(it);            // the first NST slabs of a layer find their stages free (see above)
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int c0 = s * KC + 8 * unit_idx(u);
@@ -857,7 +858,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                         if (s + 1 < nslab && c0 + KC < kreal && !(TC_DBG & 128)) tmem_ld_32x16(tsrc + (uint32_t)((s + 1) * KC), v);
                         convert(x, std::true_type{}, p);
                     }
-                    acquire(it);
+                    if (s >= (int)NST) acquire(it);            // d_ready of the previous layer already covers the first NST slabs
                     if (active) store_piece(it, p);
                     release(it);
                 }
