@@ -171,6 +171,7 @@ struct TcArgs {
     int wstage_bytes, bias_floats, region_cols, tmem_cols, nst_log2;
     int nsplit, last_npad, cout_total;          // single wide layer split into 256-column chunks over grid.y
     int f16, small;
+    int red2;                                   // the grouped-max buffer is double-buffered by tile parity (no barrier after its read-out)
     int cin0;                                   // true layer-0 width
     int tpose;                                  // grouped max: the last layer is computed transposed (channels in TMEM lanes)
     int dbg;                                    // timing probes (CAPTRA_TC_DBG): 1 no A production, 2 no W copies, 4 no MMAs, 8 no proxy fence, 64 no layer-0 gather, 128 no TMEM reads in the producers, 32 phase stamps
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
     float *bias_s = reinterpret_cast<float *>(w_stage + (size_t)NST * a.wstage_bytes);
     float *aff_s = bias_s + a.bias_floats;                                // [2][aff_pad] when a.aff_pad > 0
     float4 *meta_s = reinterpret_cast<float4 *>(aff_s + 2 * a.aff_pad + 4 * a.pre_pad);   // [2 tiles][128 rows][2]: {point, dx, dy, dz} or the assembled 8-channel row
-    float *red = reinterpret_cast<float *>(meta_s + 2 * TC_ROWS * 2);     // [4][256] partial maxima of the grouped epilogue (also the slack the
+    float *red = reinterpret_cast<float *>(meta_s + 2 * TC_ROWS * 2);     // [2 tiles][4][256] partial maxima of the grouped epilogue, double-buffered by tile parity (also the slack the
                                                                           // transposed last layer's 128-row weight reads may run into)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -883,6 +884,10 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                     // accumulators -- inv > 0, so bias and ReLU are applied to the maxima only.
                     constexpr int SEG = TC_ROWS / G;              // 32 | 64 | 128 columns per producer group
                     const int nblk = (npad + 127) / 128;
+                    // this tile's half of the buffer: the next tile writes the other half, so no barrier is needed after
+                    // the read-out below (a half is rewritten two tiles later, after everybody passed the next tile's barrier)
+                    const bool red2 = SMALL ? a.red2 != 0 : true;     // (LARGE always has room: compile-time, no extra live flag at 96 registers)
+                    float *redt = red + (red2 ? (tcnt & 1) * 1024 : 0);
                     for (int cb = 0; cb < nblk; ++cb) {
                         const uint32_t tsrc = tbase + (uint32_t)(cb * 128 + g * SEG);
                         uint32_t v0[16], v1[16];
@@ -898,7 +903,7 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                             for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(v1[j]));
                             asm volatile("" : "+f"(m));
                             if (q + 1 < SEG / 32) tmem_ld_32x16(tsrc + (uint32_t)(32 * (q + 1)), v0);
-                            red[(g * (SEG / 32) + q) * 256 + cb * 128 + r] = m;
+                            redt[(g * (SEG / 32) + q) * 256 + cb * 128 + r] = m;
                         }
                     }
                     // combine the 32-column maxima that belong to one centroid and write them out
@@ -910,11 +915,11 @@ __global__ void __launch_bounds__(tc_threads(F16, SMALL), SMALL ? 2 : 1) mlp_tc_
                         const int gi = o / npad, c = o - gi * npad;
                         const int64_t cen = (tile * TC_ROWS) / a.group + gi;
                         if (c >= cout_last || cen * a.group >= a.rows) continue;
-                        float m = red[(gi * wpg) * 256 + c];
-                        for (int w = 1; w < wpg; ++w) m = fmaxf(m, red[(gi * wpg + w) * 256 + c]);
+                        float m = redt[(gi * wpg) * 256 + c];
+                        for (int w = 1; w < wpg; ++w) m = fmaxf(m, redt[(gi * wpg + w) * 256 + c]);
                         a.out[cen * a.ldo + col_off + c] = fmaxf(fmaf(m, inv, bl[c]), 0.f);
                     }
-                    asm volatile("bar.sync 1, %0;" ::"n"(PROD) : "memory");   // red is reused by the next tile
+                    if (!red2) asm volatile("bar.sync 1, %0;" ::"n"(PROD) : "memory");   // single buffer: reused by the next tile
                 } else {
                     // row-major accumulator: the groups alternate 16-column chunks of the thread's row.  A thread
                     // owns a ROW of the accumulator, so storing it directly makes every store instruction touch 32
@@ -1077,7 +1082,7 @@ struct TcLayout {
     int nlayers, kpad[CAPTRA_MAX_MLP_LAYERS], npad[CAPTRA_MAX_MLP_LAYERS], kreal[CAPTRA_MAX_MLP_LAYERS];
     size_t off_w[CAPTRA_MAX_MLP_LAYERS], off_b[CAPTRA_MAX_MLP_LAYERS], total_floats;
     int wstage_bytes, bias_floats, nsplit, last_npad;
-    int nstages, region_cols, tmem_cols, target_occ;
+    int nstages, region_cols, tmem_cols, target_occ, red2;
     size_t smem_bytes;
     bool supported, small;
     int nchunk;
@@ -1135,6 +1140,10 @@ static TcLayout tc_layout_v(const captra_mlp_desc &d, bool f16, bool small) {
     const size_t budget = small ? (size_t)(227 * 1024) / 2 - 2048 : (size_t)225 * 1024;
     L.nstages = (!small && fixed + 4 * per_stage <= budget) ? 4 : 2;
     L.smem_bytes = fixed + (size_t)L.nstages * per_stage;
+    if (L.smem_bytes > budget) L.supported = false;
+    // a second [4][256] grouped-max buffer (double-buffered by tile parity: one barrier less per tile) where it fits
+    L.red2 = (!small || L.smem_bytes + 4096 + 4096 <= budget) ? 1 : 0;   // SMALL: only with room to spare (+ the projected-layer-0 table some launches add); LARGE: always
+    if (L.red2) L.smem_bytes += 4096;
     if (L.smem_bytes > budget) L.supported = false;
     // SMALL keeps two CTAs on an SM, so a CTA owns 256 TMEM columns: fused chains ping-pong between two regions
     // (layers <= 128 columns); a SINGLE layer needs one region and may be up to 256 columns wide (its 512-wide
@@ -1195,6 +1204,7 @@ static int tc_fill(TcArgs &a, const captra_mlp_desc *d, const void *packed, bool
     }
     a.wstage_bytes = L.wstage_bytes; a.bias_floats = L.bias_floats;
     a.region_cols = L.region_cols; a.tmem_cols = L.tmem_cols; a.nst_log2 = L.nstages == 4 ? 2 : 1;
+    a.red2 = L.red2;
     a.nsplit = L.nsplit; a.last_npad = L.last_npad; a.cout_total = d->cout[d->nlayers - 1];
     for (int l = 0; l < d->nlayers; ++l) a.kreal[l] = L.kreal[l];
     a.cin0 = d->cin;
@@ -1298,7 +1308,7 @@ static int tc_point_mlp_ex(int64_t rows, const float *segA, int64_t ldA, int ca,
     a.in_scale = in_scale; a.in_shift = in_shift; a.rows_per_cloud = rows_per_cloud;
     CAPTRA_REQUIRE(stats == nullptr || group == 0, "point_mlp: output statistics need row output (group 0)");
     a.stats = stats;
-    if (a.small && group == 0) smem -= 4096 + 8192;      // dense rows never touch the grouped-max buffer or the SA metadata ring (both sit at the end)
+    if (a.small && group == 0) smem -= 4096 + 8192 + (a.red2 ? 4096 : 0);      // dense rows never touch the grouped-max buffer or the SA metadata ring (both sit at the end)
     if (in_scale) {
         // a tile must not straddle two clouds: the kernel stages one cloud's scale/shift rows per tile
         CAPTRA_REQUIRE(rows_per_cloud % TC_ROWS == 0, "point_mlp_affine: rows_per_cloud must be a multiple of %d (got %d)", TC_ROWS, rows_per_cloud);
