@@ -46,7 +46,7 @@ cfg.update({"num_joints": P - 1, "loss_weight": {}, "pose_perturb": {"type": "no
 # the initial pose, frames 1.. are tracked
 frames, ours_frames = [], []
 for t in range(T):
-    b = track.synthetic_track_batch(B, category, n=N, seed=20 + t)
+    b = track.synthetic_track_batch(B, category, n=N, seed=20)          # a static scene: the same clouds in every frame, re-tracked from the previous estimate
     gt = {k: np.asarray(v, dtype=np.float32) for k, v in b["gt"].items()}
     labels = np.random.default_rng(t).integers(0, P + cfg["obj"]["extra_dims"], size=(B, N))
     nocs = (np.random.default_rng(100 + t).random((B, 3, N)) - 0.5).astype(np.float32)
