@@ -732,6 +732,8 @@ def main():
         # inflate each other's event-to-event time); the timed regions above ran the real two-stream frame
         for t in (list(trk.trackers.values()) if hasattr(trk, "trackers") else [trk]):
             t.TWO_STREAM = False
+        if hasattr(trk, "trackers"):
+            trk.CATEGORY_STREAMS = False
         for i in range(nprof):          # rank 0 only: no collective in here
             flush.zero_()
             r = resident[i % nb]

@@ -247,11 +247,31 @@ class MixedTracker(torch.nn.Module):
         self.trackers = torch.nn.ModuleDict(
             {c: Tracker(make_cfg(c, device=str(device)), seed=seed + 10 * (list(CATEGORIES).index(c) + 1)) for c, _, _ in self.spans})
 
+    # Each category's slice is an independent launch set on its own weights: run them on separate streams, so one
+    # category's latency-bound phases (FPS: one CTA per cloud) overlap the others' tensor work.  Matters most when a
+    # rank holds only a handful of clouds per category (cfg4 on 8 GPUs: 5-6).  CAPTRA_CATEGORY_STREAMS=0: back to back.
+    CATEGORY_STREAMS = os.environ.get("CAPTRA_CATEGORY_STREAMS", "1") != "0"
+
     @torch.no_grad()
     def step(self, points, points_mean, last_pose):
         outs = []
-        for c, a, b in self.spans:
-            outs.append(self.trackers[c].step(points[a:b], points_mean[a:b], {k: v[a:b] for k, v in last_pose.items()}))
+        concurrent = self.CATEGORY_STREAMS and points.is_cuda and len(self.spans) > 1
+        if concurrent:
+            main = torch.cuda.current_stream(points.device)
+            if not hasattr(self, "_cat_streams"):
+                self._cat_streams = [torch.cuda.Stream(points.device) for _ in self.spans]
+        for i, (c, a, b) in enumerate(self.spans):
+            args = (points[a:b], points_mean[a:b], {k: v[a:b] for k, v in last_pose.items()})
+            if concurrent:
+                st = self._cat_streams[i]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    outs.append(self.trackers[c].step(*args))
+            else:
+                outs.append(self.trackers[c].step(*args))
+        if concurrent:
+            for st in self._cat_streams:
+                main.wait_stream(st)
         if len(outs) == 1:
             return outs[0]
         return {k: torch.cat([o[k] for o in outs], dim=0) for k in outs[0]}
