@@ -342,6 +342,11 @@ def cpu_reference_arm(workload, steps, warmup, sample_clouds):
     sl = lambda d: {k: v[:one] for k, v in d.items()}
     t1 = _time_steps(lambda: frame(pts[:one], mean[:one], sl(pose)), 1, 2)
     torch.set_num_threads(cores)
+    if kind == "port":
+        cpu_ref.set_num_threads(cores)
+    # BASELINE.json configs[0]: ONE 4096-point cloud through the same CPU path (all threads)
+    sl1 = lambda d: {k: v[:1] for k, v in d.items()}
+    tb1 = _time_steps(lambda: frame(pts[:1], mean[:1], sl1(pose)), 1, 3)
     total = float(np.sum(ts))
     return {"value": sample_clouds * len(ts) / total, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": "%d of %d clouds per step x %d steps (%d warm-up), %s, torch %d threads; 1-thread figure on %d clouds x 2 steps" % (
@@ -350,7 +355,8 @@ def cpu_reference_arm(workload, steps, warmup, sample_clouds):
                 cores, one),
             "ms_per_step": 1e3 * total / len(ts), "median_ms": 1e3 * float(np.median(ts)), "best_ms": 1e3 * float(np.min(ts)),
             "frames_per_s_median": sample_clouds / float(np.median(ts)), "frames_per_s_best": sample_clouds / float(np.min(ts)),
-            "frames_per_s_1thread": one / float(np.median(t1)), "cpu_model": cpu_model_name(), "per_op_ms_1cloud": per_op,
+            "frames_per_s_1thread": one / float(np.median(t1)), "cfg1_single_cloud_ms": 1e3 * float(np.median(tb1)),
+            "cpu_model": cpu_model_name(), "per_op_ms_1cloud": per_op,
             "category": category}
 
 
