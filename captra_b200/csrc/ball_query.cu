@@ -197,7 +197,7 @@ static int launch_bq(int b, int n, int m, const BQParams &prm, const float *new_
 // ------------------------------------------------------------------------------------------------
 constexpr int BQG_DIM = 32;                    // max cells per axis
 constexpr int BQG_MAXCELL = BQG_DIM * BQG_DIM * BQG_DIM;
-constexpr int BQG_CAP = 512;                   // more hits than this: the early-exit scan is cheaper
+constexpr int BQG_CAP = 256;                   // more hits than this: the early-exit scan is cheaper
 constexpr int BQG_MAX_SMEM = 200 << 10;        // bitmap budget of the one-warp-per-CTA variant
 
 static inline int bq_grid_wpl_log2(int n) {    // bitmap words per lane (power of two) covering n bits
@@ -205,9 +205,15 @@ static inline int bq_grid_wpl_log2(int n) {    // bitmap words per lane (power o
     while ((1024ll << l) < n) ++l;
     return l;
 }
-static inline bool bq_grid_fits(int n, int nsample) {
-    return sizeof(int) * (32 * ((size_t)(1 << bq_grid_wpl_log2(n)) | 1) + (size_t)nsample) <= (size_t)BQG_MAX_SMEM;
+// A lane's run of wpl bitmap words is padded so that the lanes' runs start in different banks: wpl + 4 keeps a run 16-byte
+// aligned (the clear and the prefix pass move four words per instruction; conflict-free per quarter warp), wpl | 1 below that.
+__host__ __device__ static inline int bq_grid_stride(int wpl) { return wpl >= 4 ? wpl + 4 : (wpl | 1); }
+// per-warp working set: bitmap words + per-word prefix counts (16 bit) + per-lane offsets + hit list + staged row
+static inline size_t bq_grid_warp_bytes(int n, int nsample) {
+    const size_t words = 32 * (size_t)bq_grid_stride(1 << bq_grid_wpl_log2(n));
+    return (sizeof(int) * (words + 32 + (BQG_CAP + 32) + (size_t)nsample) + sizeof(unsigned short) * words + 15) & ~(size_t)15;
 }
+static inline bool bq_grid_fits(int n, int nsample) { return bq_grid_warp_bytes(n, nsample) <= (size_t)BQG_MAX_SMEM; }
 
 struct BQGrid {          // per cloud, written by the build kernel
     float minx, miny, minz, inv_h;
@@ -317,38 +323,64 @@ bq_grid_build_kernel(int n, float radius, const float *__restrict__ xyz, BQGrid 
 }
 
 // One warp per centroid.  Hits are recorded as bits of a per-warp index bitmap in shared memory, so
-// reading the bitmap back in word order yields them in ascending index order -- no sort.  Lane l owns
-// the wpl consecutive words [l*wpl, (l+1)*wpl), stored at an odd stride so the per-lane walks are
-// bank-conflict free.
-template <int QW>
-__global__ void __launch_bounds__(QW * 32)
-bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, const float *__restrict__ new_xyz,
-                     const float *__restrict__ xyz, const BQGrid *__restrict__ grids,
-                     const int *__restrict__ cell_start, const float4 *__restrict__ sorted, int *__restrict__ idx,
-                     int gc, const float *__restrict__ gpoints, float *__restrict__ grouped) {
-    extern __shared__ unsigned bq_smem[];
-    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = blockIdx.x * QW + warp;
-    if (ci >= m) return;
-    const int wpl = 1 << wpl_log2, stride = wpl | 1;
-    unsigned *bm = bq_smem + (size_t)warp * (32 * stride + nsample);
-    int *stage = reinterpret_cast<int *>(bm + 32 * stride);
+// the rank of a hit in index order is the number of set bits below its own -- no sort.  Lane l owns
+// the wpl consecutive words [l*wpl, (l+1)*wpl) (padded, bq_grid_stride).
+// GC: channels grouped by the query warp itself (0: none, 3: compile-time, -1: gc at run time, <= 8).
+template <int GC>
+__device__ __forceinline__ void bq_grid_centroid(int b, int ci, int lane, unsigned char *ws, int n, int m, float radius2, int nsample,
+                                                 int wpl_log2, const float *__restrict__ new_xyz, const float *__restrict__ xyz,
+                                                 const BQGrid *__restrict__ grids, const int *__restrict__ cell_start,
+                                                 const float4 *__restrict__ sorted, int *__restrict__ idx, int gc,
+                                                 const float *__restrict__ gpoints, float *__restrict__ grouped) {
+    const int wpl = 1 << wpl_log2, stride = bq_grid_stride(wpl);
+    unsigned *bm = reinterpret_cast<unsigned *>(ws);                                     // one bit per point index
+    unsigned short *pre = reinterpret_cast<unsigned short *>(bm + 32 * stride);          // set bits before each word, within its lane's run
+    int *loff = reinterpret_cast<int *>(pre + 32 * stride);                              // set bits before each lane's run of words
+    int *hits = loff + 32;                                                               // the hits in the order they were found
+    int *stage = hits + BQG_CAP + 32;                                                    // the row, in index order
     unsigned *mine = bm + lane * stride;
-    for (int j = 0; j < wpl; ++j) mine[j] = 0u;
+    if (wpl >= 4)
+        for (int j = 0; j < wpl; j += 4) *reinterpret_cast<uint4 *>(mine + j) = make_uint4(0u, 0u, 0u, 0u);
+    else
+        for (int j = 0; j < wpl; ++j) mine[j] = 0u;
     const unsigned lt = lanemask_lt();
     const BQGrid g = grids[b];
     const float *cp = new_xyz + ((size_t)b * m + ci) * 3;
     const float cx = __ldg(cp), cy = __ldg(cp + 1), cz = __ldg(cp + 2);
     int *row = idx + ((size_t)b * m + ci) * nsample;
-    // fused grouping (captra_ball_query_group, few channels): the warp that owns the row also writes
-    // grouped[b, c, ci, :] = points[b, c, row[:]] -- K contiguous floats per channel, no second launch, no idx re-read
-    auto group_row = [&](bool empty) {
-        if (!grouped) return;
-        __syncwarp();
-        for (int l = lane; l < nsample; l += 32) {
-            const int k = empty ? 0 : row[l];          // an empty ball keeps the caller's zeros: index 0
-            for (int c = 0; c < gc; ++c)
-                st_stream(grouped + (((size_t)b * gc + c) * m + ci) * nsample + l, __ldg(gpoints + ((size_t)b * gc + c) * n + k));
+    const int ngc = GC >= 0 ? GC : gc;
+    // Writes the row (keep staged indices, padded with the first hit) and, fused grouping (captra_ball_query_group, few
+    // channels), grouped[b, c, ci, :] = points[b, c, row[:]] -- K contiguous floats per channel, no second launch, no idx
+    // re-read.  An empty ball keeps the caller's zeros and groups index 0.
+    auto emit = [&](int keep) {
+        const int first = keep ? stage[0] : 0;
+        const float *src = GC ? gpoints + (size_t)b * ngc * n : nullptr;
+        float *dst = GC ? grouped + ((size_t)b * ngc * m + ci) * nsample : nullptr;
+        const size_t dstride = (size_t)m * nsample;
+        for (int l0 = lane; l0 < nsample; l0 += 64) {      // two slots per lane and pass: all their loads in flight before the first store
+            const int l1 = l0 + 32;
+            const bool two = l1 < nsample;
+            const int k0 = l0 < keep ? stage[l0] : first, k1 = two && l1 < keep ? stage[l1] : first;
+            if (keep) {
+                row[l0] = k0;
+                if (two) row[l1] = k1;
+            }
+            if (GC) {
+                constexpr int MAXC = GC > 0 ? GC : 8;
+                float v0[MAXC], v1[MAXC];
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < ngc) {
+                        v0[c] = __ldg(src + (size_t)c * n + k0);
+                        v1[c] = __ldg(src + (size_t)c * n + k1);
+                    }
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < ngc) {
+                        st_stream(dst + c * dstride + l0, v0[c]);
+                        if (two) st_stream(dst + c * dstride + l1, v1[c]);
+                    }
+            }
         }
     };
     const int *cs = cell_start + (size_t)b * (BQG_MAXCELL + 1);
@@ -357,10 +389,11 @@ bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, con
 
     int cnt = 0;
     bool overflow = false;
+    // the centroid's own cell, unclamped: a centroid outside the box still sees the right neighbours (computed ahead of
+    // the branch so that the grid descriptor and the centroid are fetched in the same round trip)
+    const int ix = (int)floorf((cx - g.minx) * g.inv_h), iy = (int)floorf((cy - g.miny) * g.inv_h),
+              iz = (int)floorf((cz - g.minz) * g.inv_h);
     if (isfinite(cx) && isfinite(cy) && isfinite(cz)) {
-        // the centroid's own cell, unclamped: a centroid outside the box still sees the right neighbours
-        const int ix = (int)floorf((cx - g.minx) * g.inv_h), iy = (int)floorf((cy - g.miny) * g.inv_h),
-                  iz = (int)floorf((cz - g.minz) * g.inv_h);
         // Cells x0..x1 of one (y,z) row are contiguous in the binned array, so the 27 cells are nine
         // segments.  Lane r < 9 fetches segment r's bounds (one round trip for all nine), and the
         // candidates are then walked as one flat list, 32 per step, with the next step's points in flight.
@@ -396,18 +429,23 @@ bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, con
             p = __ldg(pts + f + d);
             return true;
         };
-        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool have_next = fetch(lane, p_next);
+        // two steps of candidates in flight: the warp is latency-bound (shared memory caps it at ~40 warps per SM)
+        float4 p_n1 = make_float4(0.f, 0.f, 0.f, 0.f), p_n2 = p_n1;
+        bool have_n1 = fetch(lane, p_n1), have_n2 = fetch(32 + lane, p_n2);
         for (int t = 0; t < total; t += 32) {
-            const float4 p = p_next;
-            const bool have = have_next;
-            have_next = fetch(t + 32 + lane, p_next);
+            const float4 p = p_n1;
+            const bool have = have_n1;
+            p_n1 = p_n2;
+            have_n1 = have_n2;
+            have_n2 = fetch(t + 64 + lane, p_n2);
             const bool hit = have && sqdist_ref(cx, cy, cz, p.x, p.y, p.z) < radius2;
+            const unsigned bal = __ballot_sync(kFull, hit);
             if (hit) {
                 const int k = __float_as_int(p.w), w = k >> 5;
                 atomicOr(bm + (w >> wpl_log2) * stride + (w & (wpl - 1)), 1u << (k & 31));
+                hits[cnt + __popc(bal & lt)] = k;
             }
-            cnt += __popc(__ballot_sync(kFull, hit));
+            cnt += __popc(bal);
             if (cnt > BQG_CAP) { overflow = true; break; }
         }
     }
@@ -427,34 +465,71 @@ bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, con
                 have = min(nsample, have + __popc(bal));
             }
         }
+        __syncwarp();
+        if (have == 0) { emit(0); return; }
+        // (rows of this rare path are re-read from global: the same warp wrote them)
         for (int l = have + lane; l < nsample; l += 32) row[l] = first;
-        group_row(have == 0);
+        if (GC) {
+            __syncwarp();
+            for (int l = lane; l < nsample; l += 32) {
+                const int k = row[l];
+                for (int c = 0; c < ngc; ++c)
+                    st_stream(grouped + (((size_t)b * ngc + c) * m + ci) * nsample + l, __ldg(gpoints + ((size_t)b * ngc + c) * n + k));
+            }
+        }
         return;
     }
-    if (cnt == 0) { group_row(true); return; }   // empty ball: the caller's zeros stay
+    if (cnt == 0) { emit(0); return; }            // empty ball: the caller's zeros stay
     __syncwarp();
-    // ---- read the bitmap back in index order: per-lane popcount, warp prefix, ordered emission
+    // ---- index order without a sort: the rank of hit k is the number of set bits below bit k.  Per-word prefix counts
+    // within each lane's run, a warp scan across the runs, then every recorded hit looks its rank up and drops itself
+    // into the staged row.
+    unsigned short *pmine = pre + lane * stride;
     int c = 0;
-    for (int j = 0; j < wpl; ++j) c += __popc(mine[j]);
+    if (wpl >= 4) {
+        for (int j = 0; j < wpl; j += 4) {
+            const uint4 w = *reinterpret_cast<const uint4 *>(mine + j);
+            const int c1 = c + __popc(w.x), c2 = c1 + __popc(w.y), c3 = c2 + __popc(w.z);
+            *reinterpret_cast<uint2 *>(pmine + j) = make_uint2((unsigned)c | ((unsigned)c1 << 16), (unsigned)c2 | ((unsigned)c3 << 16));
+            c = c3 + __popc(w.w);
+        }
+    } else {
+        for (int j = 0; j < wpl; ++j) {
+            pmine[j] = (unsigned short)c;
+            c += __popc(mine[j]);
+        }
+    }
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(kFull, incl, o);
         if (lane >= o) incl += t;
     }
-    int pos = incl - c;
-    for (int j = 0; j < wpl && pos < nsample; ++j) {
-        unsigned w = mine[j];
-        const int base = (lane * wpl + j) << 5;
-        while (w && pos < nsample) {
-            stage[pos++] = base + __ffs(w) - 1;
-            w &= w - 1;
-        }
+    loff[lane] = incl - c;
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {
+        const int k = hits[i], w = k >> 5, own = w >> wpl_log2, slot = own * stride + (w & (wpl - 1));
+        const int r = loff[own] + pre[slot] + __popc(bm[slot] & ((1u << (k & 31)) - 1u));
+        if (r < nsample) stage[r] = k;
     }
     __syncwarp();
-    const int keep = min(cnt, nsample), first = stage[0];
-    for (int l = lane; l < nsample; l += 32) row[l] = l < keep ? stage[l] : first;
-    group_row(false);
+    emit(min(cnt, nsample));
+}
+
+// One warp per centroid (a persistent variant -- fewer CTAs, each warp striding over the centroids -- measured 4 % slower on
+// BASELINE cfg5 level 1, and capping the registers for 10 CTAs per SM spills: 364 -> 462 us).
+template <int QW, int GC>
+__global__ void __launch_bounds__(QW * 32)
+bq_grid_query_kernel(int n, int m, float radius2, int nsample, int wpl_log2, const float *__restrict__ new_xyz,
+                     const float *__restrict__ xyz, const BQGrid *__restrict__ grids,
+                     const int *__restrict__ cell_start, const float4 *__restrict__ sorted, int *__restrict__ idx,
+                     int gc, const float *__restrict__ gpoints, float *__restrict__ grouped, int warp_bytes) {
+    extern __shared__ __align__(16) unsigned char bq_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * QW + warp;
+    if (ci < m)
+        bq_grid_centroid<GC>(blockIdx.y, ci, lane, bq_smem + (size_t)warp * warp_bytes, n, m, radius2, nsample, wpl_log2, new_xyz, xyz,
+                             grids, cell_start, sorted, idx, gc, gpoints, grouped);
 }
 
 static int launch_bq_grid(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz,
@@ -498,18 +573,22 @@ static int launch_bq_grid(int b, int n, int m, float radius, int nsample, const 
     float4 *sorted = reinterpret_cast<float4 *>(ws + off_s);
     const size_t smem = sizeof(int) * (BQG_MAXCELL + 1);
     CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_query_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 << 10));
-    CAPTRA_CUDA(cudaFuncSetAttribute(bq_grid_query_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQG_MAX_SMEM));
     bq_grid_build_kernel<<<b, 1024, smem, stream>>>(n, radius, xyz, grids, cell_start, sorted);
     CAPTRA_CHECK_LAUNCH("ball_query(grid build)");
     const int wpl_log2 = bq_grid_wpl_log2(n);
-    const size_t per_warp = sizeof(int) * (32 * ((1 << wpl_log2) | 1) + (size_t)nsample);
-    if (4 * per_warp <= (64u << 10))
-        bq_grid_query_kernel<4><<<dim3(ceil_div(m, 4), b), 128, 4 * per_warp, stream>>>(
-            n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids, cell_start, sorted, idx, gc, gpoints, grouped);
-    else
-        bq_grid_query_kernel<1><<<dim3(m, b), 32, per_warp, stream>>>(
-            n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids, cell_start, sorted, idx, gc, gpoints, grouped);
+    const size_t per_warp = bq_grid_warp_bytes(n, nsample);
+    auto launch = [&](auto kern, int qw) -> int {
+        CAPTRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, qw == 4 ? (64 << 10) : BQG_MAX_SMEM));
+        kern<<<dim3(ceil_div(m, qw), b), qw * 32, qw * per_warp, stream>>>(n, m, radius * radius, nsample, wpl_log2, new_xyz, xyz, grids,
+                                                                         cell_start, sorted, idx, gc, gpoints, grouped, (int)per_warp);
+        return CAPTRA_OK;
+    };
+    const bool four = 4 * per_warp <= (64u << 10);
+    int rc;
+    if (!grouped || gc == 0) rc = four ? launch(bq_grid_query_kernel<4, 0>, 4) : launch(bq_grid_query_kernel<1, 0>, 1);
+    else if (gc == 3) rc = four ? launch(bq_grid_query_kernel<4, 3>, 4) : launch(bq_grid_query_kernel<1, 3>, 1);
+    else rc = four ? launch(bq_grid_query_kernel<4, -1>, 4) : launch(bq_grid_query_kernel<1, -1>, 1);
+    if (rc) return rc;
     CAPTRA_CHECK_LAUNCH("ball_query(grid query)");
     return CAPTRA_OK;           // ~Guard frees the scratch (stream-ordered, after the query kernel)
 }

@@ -225,6 +225,10 @@ def test_group_points_large_calls_bit_exact(b, c, n, m, k, futils, oracle, cuda)
     ("uniform", 4096, 1024, 0.1, 64),       # BASELINE cfg5 level 2
     ("uniform", 70001, 97, 0.03, 40),       # bitmap too big for four warps per CTA: one-warp variant
     ("surface", 5000, 77, 0.12, 200),       # nsample > hits for most balls, odd sizes
+    ("uniform", 2048, 2048, 0.2, 64),       # every point a centroid: crowded cells split over several work items
+    ("uniform", 16384, 4096, 0.05, 64),     # BASELINE cfg5 level 1, all 4096 centroids
+    ("clump", 6000, 1500, 0.05, 32),        # > 512 candidates around most cells: per-centroid search inside the cell kernel
+    ("same", 4096, 64, 0.05, 16),           # one cell holds everything
 ])
 def test_ball_query_grid_path_bit_exact(kind, n, m, radius, k, futils, oracle, refcu, cuda):
     """Large clouds take the binned search (csrc/ball_query.cu); same hits, same order as the scan."""
@@ -232,6 +236,10 @@ def test_ball_query_grid_path_bit_exact(kind, n, m, radius, k, futils, oracle, r
         pts = np.stack([synthetic.surface_box(n, np.random.default_rng(7 + i))[0] for i in range(2)])
     elif kind == "uniform":
         pts = synthetic.batch_uniform(2, n, seed=3)
+    elif kind == "clump":
+        pts = (0.12 * synthetic.batch_uniform(2, n, seed=5)).astype(np.float32)
+    elif kind == "same":
+        pts = np.full((2, n, 3), 0.25, np.float32)
     else:
         pts = synthetic.batch_tiled(2, n, 1234, seed=4)
     ctr = np.ascontiguousarray(pts[:, ::n // m][:, :m]).copy()
